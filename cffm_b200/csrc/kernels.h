@@ -1,0 +1,42 @@
+// Cross-file launcher declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace cffm {
+struct Model;
+
+void launch_gather_rows(const float* table, const int32_t* ids, int64_t n, int K, float* out, cudaStream_t s);
+int forward_setup_attrs(Model* m);
+int backward_setup_attrs(Model* m);
+
+// loss reduction pieces (forward.cu)
+void launch_loss_sum(Model* m, int B, cudaStream_t s);
+void launch_loss_finish(Model* m, int B, cudaStream_t s);
+
+// sparse update (update.cu)
+struct SparseWork {
+  int64_t cap = 0;
+  int32_t *keys_out = nullptr, *vals = nullptr, *vals_out = nullptr, *seg_start = nullptr, *n_uniq = nullptr;
+  uint8_t* flags = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+};
+int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err);
+void sparse_work_free(SparseWork* w);
+// sort ids, find segments; afterwards w->keys_out (sorted ids), w->vals_out (source positions),
+// w->seg_start (first sorted position of each unique row) and w->n_uniq are valid on the stream.
+int sparse_sort_segments(SparseWork* w, const int32_t* ids, int64_t n, int features_M, cudaStream_t s, int64_t* launches);
+// segment-sum the gradient rows in order of appearance and apply SparseApplyAdagrad to up to three tables
+struct SparseTables {
+  float *tab[3] = {nullptr, nullptr, nullptr};
+  float *acc[3] = {nullptr, nullptr, nullptr};
+  const float* grads[3] = {nullptr, nullptr, nullptr};
+  int K[3] = {0, 0, 0};
+};
+void launch_sparse_adagrad(const SparseWork* w, const SparseTables& t, int64_t n, float lr, cudaStream_t s, int64_t* launches);
+void launch_dense_adagrad(float* w, float* acc, const float* g, int64_t n, float lr, cudaStream_t s);
+
+}  // namespace cffm

@@ -1,0 +1,153 @@
+// Internal state behind a cffm_handle: parameter registry, device buffers, workspaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cffm.h"
+#include "kernels.h"
+
+namespace cffm {
+
+enum ParamKind { PK_DENSE = 0, PK_TABLE_INNER = 1, PK_TABLE_OUTER = 2, PK_TABLE_BIAS = 3 };
+
+struct ParamInfo {
+  std::string name;
+  int64_t shape[4];
+  int ndim;
+  int64_t numel;
+  int kind;       // ParamKind
+  int64_t offset; // into the flat dense block (PK_DENSE only)
+  bool trainable; // receives a gradient (false: dead variables)
+};
+
+constexpr int kMaxConv = 8;
+
+// Offsets (in floats) into the flat dense parameter / gradient / accumulator blocks.
+struct DenseLayout {
+  int64_t iconv_w = -1, iconv_b = -1, din_k = -1, din_b = -1;  // inner path
+  int64_t conv_w[kMaxConv], conv_b[kMaxConv];                  // outer conv stack
+  int64_t outer_W = -1, outer_b = -1;                          // dead
+  int64_t d1_k = -1, d1_b = -1, d2_k = -1, d2_b = -1;          // outer head
+  int64_t att_W = -1, att_b = -1, d3_k = -1, d3_b = -1;        // linear attention
+  int64_t bias = -1;
+  int64_t total = 0;
+};
+
+struct Comm;  // NCCL state (comm.cu)
+
+struct Model {
+  cffm_config cfg;
+  int F, P, Ki, Ko, M;
+  int conv_depth;  // int(log2 Ko), CFFM.py:373
+  int n_live;      // conv layers that reach the output = conv_depth - 1
+  int t1_dim;      // sum_{l<conv_depth} Ko >> l   (= 2K-2)
+  int max_batch;
+  int device;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  std::vector<ParamInfo> params;
+  DenseLayout lay;
+
+  // parameters + Adagrad accumulators
+  float *inner_tab = nullptr, *outer_tab = nullptr, *fbias_tab = nullptr;
+  float *inner_acc = nullptr, *outer_acc = nullptr, *fbias_acc = nullptr;
+  float *dense_w = nullptr, *dense_acc = nullptr, *dense_g = nullptr;
+
+  // pair tables
+  int *pair_i = nullptr, *pair_j = nullptr;  // [P]
+
+  // ---- forward workspaces (sized by max_batch) ----
+  int32_t* ids_buf = nullptr;   // [B,F] staging for host entry points (device)
+  float* labels_buf = nullptr;  // [B]
+  float* outer_rows = nullptr;  // [B,F,Ko] gathered outer rows
+  float* Y[kMaxConv] = {};      // pre-activation conv outputs, NHWC [B,H_l+1,H_l+1,P]
+  float* t1 = nullptr;          // [B,t1_dim]
+  float* hid = nullptr;         // [B,32]
+  float* comp_inner = nullptr;  // [B] final2
+  float* comp_outer = nullptr;  // [B] final (after beta)
+  float* comp_lin = nullptr;    // [B]
+  float* out = nullptr;         // [B] raw sum (pre-sigmoid)
+  float* pred = nullptr;        // [B] what sess.run(self.out) returns
+  float* loss_terms = nullptr;  // [B]
+  float* scalars = nullptr;     // [16] device scalars: 0 loss sum, 1 loss, 2 gscale, 3 global B ...
+  float* loss_out = nullptr;    // [1]
+
+  // ---- backward workspaces (allocated on first train step) ----
+  bool train_ready = false;
+  float* gout = nullptr;          // [B] dLoss/dout_raw
+  float* dY[kMaxConv] = {};       // gradients w.r.t. Y_l
+  float* g_inner_rows = nullptr;  // [B,F,Ki]
+  float* g_outer_rows = nullptr;  // [B,F,Ko]
+  float* g_bias_rows = nullptr;   // [B,F]
+  float* v_head = nullptr;        // [t1_dim] W1.W2
+  float* rowbuf = nullptr;        // [B, n_small] per-sample rows to be column-summed
+  int n_small = 0;
+  float* partials = nullptr;      // scratch for split reductions
+  int64_t partials_cap = 0;
+  int64_t aux_off = 0;            // start of the aux sums region inside dense_g: q[t1_dim], G, rowsums[n_small]
+  void* reduce_descs = nullptr;   // device array of ReduceDesc
+  int n_reduce_descs = 0;
+  float* fb_buf = nullptr;        // [B,F] gathered feature_bias
+
+  // ---- sparse update workspaces ----
+  int64_t upd_cap = 0;            // capacity in ids (world * max_batch * F)
+  int32_t *all_ids = nullptr;     // [upd_cap] ids of the global batch (== ids when world==1)
+  float *all_g_inner = nullptr, *all_g_outer = nullptr, *all_g_bias = nullptr;  // gathered grads (DP)
+  SparseWork sw;                  // sort / segment scratch
+
+  // ---- host staging (pinned) ----
+  int32_t* h_ids[2] = {nullptr, nullptr};
+  float* h_labels[2] = {nullptr, nullptr};
+  float* h_loss[2] = {nullptr, nullptr};
+  float* h_out = nullptr;
+  cudaEvent_t slot_done[2] = {nullptr, nullptr};
+  int pending = 0;   // submitted-but-unreported steps (0..1)
+  int slot = 0;
+
+  // ---- CUDA graph cache for the train step (keyed by B) ----
+  cudaGraphExec_t step_graph = nullptr;
+  int64_t step_graph_B = -1;
+  int64_t step_graph_launches = 0;
+
+  Comm* comm = nullptr;
+  int world = 1, rank = 0;
+  int64_t last_B = 0;       // batch of the last forward / train step (for cffm_debug_fetch)
+  bool use_graph = true;    // CFFM_GRAPH=0 disables CUDA-graph replay of the train step
+
+  // evaluate scratch
+  double* eval_acc = nullptr;  // [8] device doubles
+};
+
+// ---- implemented across the .cu files ----
+int model_build_layout(Model* m);
+int model_alloc(Model* m);
+int model_alloc_train(Model* m);
+void model_free(Model* m);
+int model_init_params(Model* m, uint64_t seed);
+const ParamInfo* model_find(const Model* m, const char* name);
+
+// labels == nullptr: scoring only; otherwise loss terms and dLoss/dout are produced as well
+int run_forward(Model* m, const int32_t* ids_dev, const float* labels_dev, int64_t B, cudaStream_t s);
+int run_backward_update(Model* m, const int32_t* ids_dev, const float* labels_dev, int64_t B, cudaStream_t s);
+
+int comm_allreduce_f32(Model* m, float* buf, int64_t n, cudaStream_t s);
+int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s);
+void comm_destroy(Model* m);
+
+#define CFFM_CUDA_OK(m, call)                                                                 \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      (m)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                          \
+      return CFFM_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace cffm
+
+struct cffm_handle { cffm::Model m; };
