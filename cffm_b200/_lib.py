@@ -118,6 +118,8 @@ def _declare(lib):
         "cffm_evaluate_host": (C.c_int, [vp, vp, vp, i64, i64, P(C.c_double), P(C.c_double)]),
         "cffm_synchronize": (C.c_int, [vp]),
         "cffm_launch_count": (i64, [vp]),
+        "cffm_profile_enable": (C.c_int, [vp, i32]),
+        "cffm_profile_report": (i64, [vp, C.c_char_p, i64, i32]),
         "cffm_op_gather_dev": (C.c_int, [vp, vp, i64, i32, vp, vp]),
         "cffm_op_sparse_adagrad_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, i64, f32, vp, vp, vp]),
         "cffm_debug_fetch": (C.c_int, [vp, C.c_char_p, vp, i64, P(i64)]),

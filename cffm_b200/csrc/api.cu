@@ -80,6 +80,54 @@ extern "C" int cffm_synchronize(cffm_handle* h) {
 
 extern "C" int64_t cffm_launch_count(const cffm_handle* h) { return h ? h->m.launches : 0; }
 
+// ---- per-kernel timing ------------------------------------------------------------------------
+namespace cffm {
+ProfScope::ProfScope(Model* m_, const char* tag, cudaStream_t s_) : m(m_), s(s_), idx(-1) {
+  if (!m->prof_on) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  Model::ProfEv ev;
+  ev.tag = tag;
+  for (cudaEvent_t* e : {&ev.a, &ev.b}) {
+    if (!m->prof_pool.empty()) { *e = m->prof_pool.back(); m->prof_pool.pop_back(); }
+    else if (cudaEventCreate(e) != cudaSuccess) return;
+  }
+  cudaEventRecord(ev.a, s);
+  m->prof_pending.push_back(ev);
+  idx = (int)m->prof_pending.size() - 1;
+}
+ProfScope::~ProfScope() { if (idx >= 0) cudaEventRecord(m->prof_pending[idx].b, s); }
+}  // namespace cffm
+
+extern "C" int cffm_profile_enable(cffm_handle* h, int32_t on) {
+  if (!h) return CFFM_ERR_INVALID;
+  h->m.prof_on = on != 0;
+  return CFFM_OK;
+}
+
+extern "C" int64_t cffm_profile_report(cffm_handle* h, char* buf, int64_t cap, int32_t reset) {
+  if (!h) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (auto& ev : m->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { auto& acc = m->prof_acc[ev.tag]; acc.first += 1; acc.second += ms; }
+    m->prof_pool.push_back(ev.a); m->prof_pool.push_back(ev.b);
+  }
+  m->prof_pending.clear();
+  cudaGetLastError();
+  std::string out;
+  for (auto& kv : m->prof_acc) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) { strncpy(buf, out.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  if (reset) m->prof_acc.clear();
+  return (int64_t)out.size() + 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" int cffm_param_count(const cffm_handle* h) { return h ? (int)h->m.params.size() : CFFM_ERR_INVALID; }
 
@@ -182,6 +230,8 @@ static int train_step_on(Model* m, const int32_t* ids, const float* labels, int6
   return run_backward_update(m, ids, labels, B, s);
 }
 
+static int enqueue_staged_step(Model* m, int64_t B, cudaStream_t run_stream);
+
 extern "C" int cffm_train_step_dev(cffm_handle* h, const int32_t* ids_dev, const float* labels_dev, int64_t B,
                                    float* loss_dev, void* stream) {
   API_BEGIN
@@ -191,7 +241,15 @@ extern "C" int cffm_train_step_dev(cffm_handle* h, const int32_t* ids_dev, const
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   r = model_alloc_train(m); if (r != CFFM_OK) return r;
   cudaStream_t s = (cudaStream_t)stream;
-  r = train_step_on(m, ids_dev, labels_dev, B, s); if (r != CFFM_OK) return r;
+  if (m->use_graph && !m->prof_on) {
+    // stage into the library's buffers (device-to-device) so that the step can replay from its CUDA graph
+    CFFM_CUDA_OK(m, cudaMemcpyAsync(m->ids_buf, ids_dev, sizeof(int32_t) * B * m->F, cudaMemcpyDeviceToDevice, s));
+    CFFM_CUDA_OK(m, cudaMemcpyAsync(m->labels_buf, labels_dev, sizeof(float) * B, cudaMemcpyDeviceToDevice, s));
+    r = enqueue_staged_step(m, B, s);
+  } else {
+    r = train_step_on(m, ids_dev, labels_dev, B, s);
+  }
+  if (r != CFFM_OK) return r;
   if (loss_dev) { k_copy_f32<<<1, 32, 0, s>>>(m->loss_out, loss_dev, 1); m->launches++; }
   m->last_B = B;
   CFFM_CUDA_OK(m, cudaGetLastError());
@@ -201,9 +259,10 @@ extern "C" int cffm_train_step_dev(cffm_handle* h, const int32_t* ids_dev, const
 
 // Enqueue one step that reads the device staging buffers; replayed from a CUDA graph when the
 // batch size repeats (the reference loop uses one fixed batch size, CFFM.py:186-200).
-static int enqueue_staged_step(Model* m, int64_t B) {
+static int enqueue_staged_step(Model* m, int64_t B, cudaStream_t run_stream) {
+  if (m->prof_on) return train_step_on(m, m->ids_buf, m->labels_buf, B, run_stream);  // eager, event-bracketed
   if (m->use_graph && m->step_graph && m->step_graph_B == B) {
-    CFFM_CUDA_OK(m, cudaGraphLaunch(m->step_graph, m->stream));
+    CFFM_CUDA_OK(m, cudaGraphLaunch(m->step_graph, run_stream));
     m->launches += m->step_graph_launches;
     return CFFM_OK;
   }
@@ -221,7 +280,7 @@ static int enqueue_staged_step(Model* m, int64_t B) {
         m->step_graph_B = B;
         m->step_graph_launches = m->launches - before;
         m->launches = before;
-        CFFM_CUDA_OK(m, cudaGraphLaunch(m->step_graph, m->stream));
+        CFFM_CUDA_OK(m, cudaGraphLaunch(m->step_graph, run_stream));
         m->launches += m->step_graph_launches;
         return CFFM_OK;
       }
@@ -232,7 +291,7 @@ static int enqueue_staged_step(Model* m, int64_t B) {
     m->use_graph = false;  // capture is not possible here: run eagerly from now on
     if (r != CFFM_OK) return r;
   }
-  return train_step_on(m, m->ids_buf, m->labels_buf, B, m->stream);
+  return train_step_on(m, m->ids_buf, m->labels_buf, B, run_stream);
 }
 
 static int submit(Model* m, const int32_t* ids_host, const float* labels_host, int64_t B) {
@@ -244,7 +303,7 @@ static int submit(Model* m, const int32_t* ids_host, const float* labels_host, i
   memcpy(m->h_labels[sl], labels_host, sizeof(float) * B);
   CFFM_CUDA_OK(m, cudaMemcpyAsync(m->ids_buf, m->h_ids[sl], sizeof(int32_t) * B * F, cudaMemcpyHostToDevice, m->stream));
   CFFM_CUDA_OK(m, cudaMemcpyAsync(m->labels_buf, m->h_labels[sl], sizeof(float) * B, cudaMemcpyHostToDevice, m->stream));
-  int r = enqueue_staged_step(m, B); if (r != CFFM_OK) return r;
+  int r = enqueue_staged_step(m, B, m->stream); if (r != CFFM_OK) return r;
   CFFM_CUDA_OK(m, cudaMemcpyAsync(m->h_loss[sl], m->loss_out, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   CFFM_CUDA_OK(m, cudaEventRecord(m->slot_done[sl], m->stream));
   m->last_B = B;

@@ -3,6 +3,7 @@
 // fixed-order two-stage sum (chunk partials, then chunks in order) so a step is reproducible.
 #include <stdio.h>
 
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -519,6 +520,7 @@ static void launch_gemm(Model* m, const Prob& prob, int nsplit, cudaStream_t s) 
 
 static void launch_colsum(Model* m, const float* X, int64_t rows, int ld, int n, const float* wgt, float* partial, int C,
                           cudaStream_t s) {
+  CFFM_PROF(m, "colsum", s);
   dim3 grid(ceil_div(n, 32), C);
   k_colsum<<<grid, 256, 0, s>>>(X, rows, ld, n, wgt, partial, C);
   m->launches++;
@@ -544,7 +546,8 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   launch_colsum(m, m->gout, B, 1, 1, nullptr, part + pl.off_G, pl.Cb, s);
   if (m->cfg.outer_conv) {
     const int K = m->Ko;
-    k_head_prep<<<1, 128, 0, s>>>(w + L.d1_k, w + L.d2_k, m->cfg.beta_outer, m->t1_dim, m->v_head);
+    { CFFM_PROF(m, "head_prep", s);
+    k_head_prep<<<1, 128, 0, s>>>(w + L.d1_k, w + L.d2_k, m->cfg.beta_outer, m->t1_dim, m->v_head); }
     m->launches++;
     launch_colsum(m, m->t1, B, m->t1_dim, m->t1_dim, m->gout, part + pl.off_q, pl.Cb, s);
     // offsets of the pooling levels inside t1
@@ -555,6 +558,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
       const int l = m->n_live - 1;
       const int H = K >> (l + 1);
       const int64_t total = (int64_t)B * H * H * P;
+      CFFM_PROF(m, "dy_top", s);
       CFFM_DISPATCH_ACT(act, k_dy_top<ACT><<<ceil_div(total, 256), 256, 0, s>>>(
           m->Y[l], m->gout, m->v_head + lvl_off[l + 1], H, P, total, m->dY[l]));
       m->launches++;
@@ -563,19 +567,20 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
       const int Hin = K >> l, Ho = Hin >> 1;
       const int rows = B * Ho * Ho;
       launch_colsum(m, m->dY[l], rows, P, P, nullptr, part + pl.off_bg[l], pl.Cl[l], s);
+      const std::string tag_w = "conv_wgrad_l" + std::to_string(l), tag_d = "conv_dgrad_l" + std::to_string(l);
       if (l > 0) {
         CFFM_DISPATCH_ACT(act, {
           ConvWgradProb<ACT> wp;
           wp.M = 4 * P; wp.N = P; wp.Kd = rows;
           wp.g.P = P; wp.g.Hin = Hin; wp.g.lgHo = ilog2(Ho);
           wp.Yprev = m->Y[l - 1]; wp.dY = m->dY[l]; wp.partial = part + pl.off_wg[l];
-          launch_gemm(m, wp, pl.nsplit[l], s);
+          { CFFM_PROF(m, tag_w.c_str(), s); launch_gemm(m, wp, pl.nsplit[l], s); }
           ConvDgradProb<ACT> dp;
           dp.M = rows; dp.N = 4 * P; dp.Kd = P;
           dp.g.P = P; dp.g.Hin = Hin; dp.g.lgHo = ilog2(Ho);
           dp.dY = m->dY[l]; dp.W = w + L.conv_w[l]; dp.Yprev = m->Y[l - 1]; dp.dYprev = m->dY[l - 1];
           dp.gout = m->gout; dp.v_head = m->v_head; dp.sp_off = lvl_off[l];
-          launch_gemm(m, dp, 1, s);
+          { CFFM_PROF(m, tag_d.c_str(), s); launch_gemm(m, dp, 1, s); }
         });
       } else {
         Conv0WgradProb wp;
@@ -583,11 +588,12 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
         wp.g.P = P; wp.g.F = F; wp.g.K = K; wp.g.lgHo = ilog2(Ho);
         wp.g.rows = m->outer_rows; wp.g.pair_i = m->pair_i; wp.g.pair_j = m->pair_j;
         wp.dY = m->dY[0]; wp.partial = part + pl.off_wg[0];
-        launch_gemm(m, wp, pl.nsplit[0], s);
+        { CFFM_PROF(m, tag_w.c_str(), s); launch_gemm(m, wp, pl.nsplit[0], s); }
         Dgrad0Args da;
         da.dY0 = m->dY[0]; da.W0 = w + L.conv_w[0]; da.rows = m->outer_rows; da.gout = m->gout; da.v_head = m->v_head;
         da.pair_i = m->pair_i; da.pair_j = m->pair_j; da.g_rows = m->g_outer_rows;
         da.F = F; da.P = P; da.K = K; da.lgHo = ilog2(Ho);
+        CFFM_PROF(m, tag_d.c_str(), s);
         k_dgrad0<<<B, Ho * Ho, dgrad0_smem(F, K), s>>>(da);
         m->launches++;
       }
@@ -604,7 +610,8 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     a.g_inner_rows = m->g_inner_rows; a.g_bias_rows = m->g_bias_rows; a.rowbuf = m->rowbuf;
     int wpb = 8;
     while (wpb > 1 && inner_bwd_smem(F, P, a.K, wpb) > 96 * 1024) wpb >>= 1;
-    CFFM_DISPATCH_ACT(act, k_inner_linear_bwd<ACT><<<ceil_div(B, wpb), wpb * 32, inner_bwd_smem(F, P, a.K, wpb), s>>>(a));
+    { CFFM_PROF(m, "inner_linear_bwd", s);
+    CFFM_DISPATCH_ACT(act, k_inner_linear_bwd<ACT><<<ceil_div(B, wpb), wpb * 32, inner_bwd_smem(F, P, a.K, wpb), s>>>(a)); }
     m->launches++;
     launch_colsum(m, m->rowbuf, B, m->n_small, m->n_small, nullptr, part + pl.off_rows, pl.Cb, s);
     if (m->cfg.inner_conv) {
@@ -613,11 +620,13 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
       d.tab = m->inner_tab; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
       d.pair_i = m->pair_i; d.pair_j = m->pair_j; d.partial = part + pl.off_Wd; d.C = pl.Cb;
       dim3 grid(ceil_div((int64_t)P * m->Ki, 256), pl.Cb);
+      CFFM_PROF(m, "inner_dense_grad", s);
       CFFM_DISPATCH_ACT(act, k_inner_dense_grad<ACT><<<grid, 256, 0, s>>>(d));
       m->launches++;
     }
     if (m->cfg.linear_att) {
       dim3 grid(ceil_div(F * F, 256), pl.Cb);
+      CFFM_PROF(m, "att_outer", s);
       k_att_outer<<<grid, 256, 0, s>>>(m->fb_buf, m->rowbuf, B, F, m->n_small, part + pl.off_attW, pl.Cb);
       m->launches++;
     }
@@ -625,7 +634,8 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   // ---- fold the partial sums into the dense gradient block, then the derived head gradients ----
   {
     dim3 grid(2 * 148, m->n_reduce_descs);
-    k_reduce_partials<<<grid, 256, 0, s>>>((const ReduceDesc*)m->reduce_descs, part, g);
+    { CFFM_PROF(m, "reduce_partials", s);
+    k_reduce_partials<<<grid, 256, 0, s>>>((const ReduceDesc*)m->reduce_descs, part, g); }
     m->launches++;
     HeadGradArgs h;
     h.F = F; h.t1_dim = m->t1_dim; h.inner_conv = m->cfg.inner_conv; h.outer_conv = m->cfg.outer_conv;
@@ -633,6 +643,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     h.W1 = w + L.d1_k; h.b1 = w + L.d1_b; h.W2 = w + L.d2_k; h.aux = g + m->aux_off; h.g = g;
     h.d1_k = L.d1_k; h.d1_b = L.d1_b; h.d2_k = L.d2_k; h.d2_b = L.d2_b; h.bias = L.bias; h.din_b = L.din_b;
     h.d3_k = L.d3_k; h.d3_b = L.d3_b; h.att_b = L.att_b; h.iconv_w = L.iconv_w; h.iconv_b = L.iconv_b;
+    CFFM_PROF(m, "head_grads", s);
     k_head_grads<<<1, 256, 0, s>>>(h);
     m->launches++;
   }
@@ -641,6 +652,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   const float *gi = m->g_inner_rows, *go = m->g_outer_rows, *gbr = m->g_bias_rows;
   int64_t n_upd = (int64_t)B * F;
   if (m->world > 1) {
+    CFFM_PROF(m, "dp_allreduce_allgather", s);
     int r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) return r;
     r = comm_allgather(m, ids, m->all_ids, sizeof(int32_t) * n_upd, s); if (r != CFFM_OK) return r;
     if (m->cfg.inner_conv) { r = comm_allgather(m, gi, m->all_g_inner, sizeof(float) * n_upd * m->Ki, s); if (r != CFFM_OK) return r; }
@@ -651,17 +663,19 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   }
   // ---- sparse update of the three tables (one sort shared by all of them) ----
   {
-    int r = sparse_sort_segments(&m->sw, upd_ids, n_upd, m->M, s, &m->launches);
+    int r;
+    { CFFM_PROF(m, "sort_segments", s); r = sparse_sort_segments(&m->sw, upd_ids, n_upd, m->M, s, &m->launches); }
     if (r != CFFM_OK) { m->err = "sparse_sort_segments failed"; return r; }
     SparseTables t;
     int j = 0;
     if (m->cfg.inner_conv) { t.tab[j] = m->inner_tab; t.acc[j] = m->inner_acc; t.grads[j] = gi; t.K[j] = m->Ki; ++j; }
     if (m->cfg.outer_conv) { t.tab[j] = m->outer_tab; t.acc[j] = m->outer_acc; t.grads[j] = go; t.K[j] = m->Ko; ++j; }
     t.tab[j] = m->fbias_tab; t.acc[j] = m->fbias_acc; t.grads[j] = gbr; t.K[j] = 1; ++j;
+    CFFM_PROF(m, "sparse_adagrad", s);
     launch_sparse_adagrad(&m->sw, t, n_upd, m->cfg.lr, s, &m->launches);
   }
   // ---- dense update ----
-  launch_dense_adagrad(m->dense_w, m->dense_acc, g, L.total, m->cfg.lr, s);
+  { CFFM_PROF(m, "dense_adagrad", s); launch_dense_adagrad(m->dense_w, m->dense_acc, g, L.total, m->cfg.lr, s); }
   m->launches++;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;

@@ -1,6 +1,8 @@
 // Forward pass of the CFFM graph (CFFM.py:296-453) + loss terms (CFFM.py:486-514).
 #include <stdio.h>
 
+#include <string>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.h"
@@ -251,11 +253,13 @@ __global__ void k_loss_finish(float* __restrict__ scalars, int loss_type, float 
 }
 
 void launch_loss_sum(Model* m, int B, cudaStream_t s) {
+  CFFM_PROF(m, "loss_sum", s);
   k_loss_sum<<<1, 1024, 0, s>>>(m->loss_terms, B, m->scalars);
   m->launches++;
 }
 void launch_loss_finish(Model* m, int B, cudaStream_t s) {
   const float invB = 1.f / (float)((int64_t)B * m->world);
+  CFFM_PROF(m, "loss_finish", s);
   k_loss_finish<<<ceil_div(B, 256), 256, 0, s>>>(m->scalars, m->cfg.loss_type, invB, m->gout, B, m->loss_out);
   m->launches++;
 }
@@ -301,6 +305,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
     int wpb = 8;
     while (wpb > 1 && inner_smem(F, P, a.K, wpb) > 96 * 1024) wpb >>= 1;
     const size_t smem = inner_smem(F, P, a.K, wpb);
+    CFFM_PROF(m, "inner_linear_fwd", s);
     CFFM_DISPATCH_ACT(m->cfg.activation,
       k_inner_linear_fwd<ACT><<<ceil_div(B, wpb), wpb * 32, smem, s>>>(a));
     m->launches++;
@@ -308,14 +313,17 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
   // ---- outer path ----
   if (m->cfg.outer_conv) {
     const int K = m->Ko;
-    launch_gather_rows(m->outer_tab, ids, (int64_t)B * F, K, m->outer_rows, s);
+    { CFFM_PROF(m, "gather_outer", s); launch_gather_rows(m->outer_tab, ids, (int64_t)B * F, K, m->outer_rows, s); }
     m->launches++;
+    CFFM_PROF(m, "sumpool0", s);
     k_sumpool0<<<ceil_div(B, 8), 256, 8 * 2 * F * sizeof(float), s>>>(m->outer_rows, B, F, K, m->t1, m->t1_dim);
     m->launches++;
     int off = K;
     for (int l = 0; l < m->n_live; ++l) {
       const int Hin = K >> l, Ho = Hin >> 1;
+      const std::string tag_f = "conv_fwd_l" + std::to_string(l), tag_s = "sumpool_l" + std::to_string(l + 1);
       if (l == 0) {
+        CFFM_PROF(m, tag_f.c_str(), s);
         Conv0FwdProb pr;
         pr.M = B * Ho * Ho; pr.N = P; pr.Kd = 4 * P;
         pr.g.P = P; pr.g.F = F; pr.g.K = K; pr.g.lgHo = ilog2(Ho);
@@ -323,6 +331,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
         pr.W = w + L.conv_w[0]; pr.bias = w + L.conv_b[0]; pr.Yout = m->Y[0];
         launch_gemm(m, pr, 1, s);
       } else {
+        CFFM_PROF(m, tag_f.c_str(), s);
         CFFM_DISPATCH_ACT(m->cfg.activation, {
           ConvFwdProb<ACT> pr;
           pr.M = B * Ho * Ho; pr.N = P; pr.Kd = 4 * P;
@@ -332,6 +341,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
         });
       }
       const int64_t BH = (int64_t)B * Ho;
+      CFFM_PROF(m, tag_s.c_str(), s);
       CFFM_DISPATCH_ACT(m->cfg.activation,
         k_sumpool<ACT><<<ceil_div(BH * 32, 256), 256, 0, s>>>(m->Y[l], BH, Ho, P, m->t1, m->t1_dim, off));
       m->launches++;
@@ -348,6 +358,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
     a.invB = 1.f / (float)((int64_t)B * m->world);
     a.comp_outer = m->comp_outer; a.out = m->out; a.pred = m->pred;
     a.labels = labels; a.loss_terms = m->loss_terms; a.gout = m->gout;
+    CFFM_PROF(m, "head_fwd", s);
     k_head_fwd<<<ceil_div((int64_t)B * 32, 256), 256, 0, s>>>(a);
     m->launches++;
   }

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cffm.h"
@@ -116,6 +118,12 @@ struct Model {
 
   Comm* comm = nullptr;
   int world = 1, rank = 0;
+  // per-kernel CUDA-event timing (cffm_profile_enable / cffm_profile_report)
+  bool prof_on = false;
+  struct ProfEv { std::string tag; cudaEvent_t a, b; };
+  std::vector<ProfEv> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::map<std::string, std::pair<int64_t, double>> prof_acc;  // tag -> (launches, total ms)
   int64_t last_B = 0;       // batch of the last forward / train step (for cffm_debug_fetch)
   bool use_graph = true;    // CFFM_GRAPH=0 disables CUDA-graph replay of the train step
 
@@ -138,6 +146,14 @@ int run_backward_update(Model* m, const int32_t* ids_dev, const float* labels_de
 int comm_allreduce_f32(Model* m, float* buf, int64_t n, cudaStream_t s);
 int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s);
 void comm_destroy(Model* m);
+
+// Brackets one launch with CUDA events on its stream when profiling is enabled.
+struct ProfScope {
+  Model* m; cudaStream_t s; int idx;
+  ProfScope(Model* m_, const char* tag, cudaStream_t s_);
+  ~ProfScope();
+};
+#define CFFM_PROF(m, tag, s) ProfScope _prof_scope_##__LINE__((m), (tag), (s))
 
 #define CFFM_CUDA_OK(m, call)                                                                 \
   do {                                                                                        \

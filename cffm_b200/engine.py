@@ -78,15 +78,21 @@ class Engine:
             self._params = out
         return self._params
 
+    def _info(self, name):
+        infos = self.param_infos()
+        if name not in infos:
+            raise CffmError("unknown variable: %s" % (name,))
+        return infos[name]
+
     def get_param(self, name, accum=False):
-        shape, numel, _ = self.param_infos()[name]
+        shape, numel, _ = self._info(name)
         a = np.empty(numel, dtype=np.float32)
         fn = self.lib.cffm_get_accum if accum else self.lib.cffm_get_param
         self._check(fn(self.h, name.encode(), _ptr(a), numel), "cffm_get_param")
         return a.reshape(shape)
 
     def set_param(self, name, value, accum=False):
-        shape, numel, _ = self.param_infos()[name]
+        shape, numel, _ = self._info(name)
         a = np.ascontiguousarray(np.asarray(value, dtype=np.float32).reshape(-1))
         if a.size != numel:
             raise CffmError("size mismatch for %s: %d vs %d" % (name, a.size, numel))
@@ -160,6 +166,19 @@ class Engine:
     def synchronize(self):
         self._check(self.lib.cffm_synchronize(self.h), "cffm_synchronize")
 
+    def profile(self, on=True):
+        self._check(self.lib.cffm_profile_enable(self.h, 1 if on else 0), "cffm_profile_enable")
+
+    def profile_report(self, reset=True):
+        """{tag: (launches, total_ms)} of the event-bracketed launches since the last reset."""
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.cffm_profile_report(self.h, buf, len(buf), 1 if reset else 0)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms = line.split()
+            out[tag] = (int(n), float(ms))
+        return out
+
     def launch_count(self):
         return int(self.lib.cffm_launch_count(self.h))
 
@@ -172,7 +191,7 @@ class Engine:
         return a
 
     def dense_grad(self, name):
-        shape, numel, _ = self.param_infos()[name]
+        shape, numel, _ = self._info(name)
         a = np.empty(numel, dtype=np.float32)
         self._check(self.lib.cffm_debug_dense_grad(self.h, name.encode(), _ptr(a), numel), "cffm_debug_dense_grad")
         return a.reshape(shape)

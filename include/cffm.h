@@ -142,6 +142,13 @@ int cffm_synchronize(cffm_handle* h);
 /* number of kernels launched by the library on this handle since creation */
 int64_t cffm_launch_count(const cffm_handle* h);
 
+/* ---- per-kernel device timing: while enabled every launch of the library is bracketed by CUDA
+ *      events on its stream (steps run eagerly, not from the CUDA graph).  cffm_profile_report
+ *      synchronises and writes one line per kernel tag: "<tag> <launches> <total_ms>\n";
+ *      returns the buffer size needed. */
+int cffm_profile_enable(cffm_handle* h, int32_t on);
+int64_t cffm_profile_report(cffm_handle* h, char* buf, int64_t cap, int32_t reset);
+
 /* ---- operator-level entry points (the gather / scatter halves of the path) ----------------- */
 /* tf.nn.embedding_lookup (CFFM.py:303, :354, :422): out[n, K] = table[ids[n], :] */
 int cffm_op_gather_dev(const float* table_dev, const int32_t* ids_dev, int64_t n, int32_t K,
