@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcffm_b200.so")
 BUILD_DIR = os.path.join(ROOT, "build")
 
-CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu"]
+CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu", "gemm_tc.cu"]
 CPP_SOURCES = ["libfm.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -122,6 +122,8 @@ def _declare(lib):
         "cffm_profile_report": (i64, [vp, C.c_char_p, i64, i32]),
         "cffm_op_gather_dev": (C.c_int, [vp, vp, i64, i32, vp, vp]),
         "cffm_op_sparse_adagrad_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, i64, f32, vp, vp, vp]),
+        "cffm_op_gemm_bf16_dev": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
+        "cffm_tc_last_error": (C.c_char_p, []),
         "cffm_debug_fetch": (C.c_int, [vp, C.c_char_p, vp, i64, P(i64)]),
         "cffm_debug_dense_grad": (C.c_int, [vp, C.c_char_p, vp, i64]),
         "cffm_comm_unique_id": (C.c_int, [C.c_char_p]),

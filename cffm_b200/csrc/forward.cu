@@ -315,8 +315,8 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
     const int K = m->Ko;
     { CFFM_PROF(m, "gather_outer", s); launch_gather_rows(m->outer_tab, ids, (int64_t)B * F, K, m->outer_rows, s); }
     m->launches++;
-    CFFM_PROF(m, "sumpool0", s);
-    k_sumpool0<<<ceil_div(B, 8), 256, 8 * 2 * F * sizeof(float), s>>>(m->outer_rows, B, F, K, m->t1, m->t1_dim);
+    { CFFM_PROF(m, "sumpool0", s);
+    k_sumpool0<<<ceil_div(B, 8), 256, 8 * 2 * F * sizeof(float), s>>>(m->outer_rows, B, F, K, m->t1, m->t1_dim); }
     m->launches++;
     int off = K;
     for (int l = 0; l < m->n_live; ++l) {

@@ -153,7 +153,9 @@ struct ProfScope {
   ProfScope(Model* m_, const char* tag, cudaStream_t s_);
   ~ProfScope();
 };
-#define CFFM_PROF(m, tag, s) ProfScope _prof_scope_##__LINE__((m), (tag), (s))
+#define CFFM_PROF_CAT2(a, b) a##b
+#define CFFM_PROF_CAT(a, b) CFFM_PROF_CAT2(a, b)
+#define CFFM_PROF(m, tag, s) ProfScope CFFM_PROF_CAT(_prof_scope_, __LINE__)((m), (tag), (s))
 
 #define CFFM_CUDA_OK(m, call)                                                                 \
   do {                                                                                        \

@@ -1,0 +1,170 @@
+// Warp-specialised tcgen05 pipeline shared by every tensor-core kernel of the conv stack.
+//
+//   warp 0        : TMA producer (one elected lane): operand tiles -> shared memory stages
+//   warp 1        : MMA issuer (lane 0): tcgen05.mma over the stages, accumulators in TMEM
+//   warps 2..5    : epilogue: tcgen05.ld TMEM -> registers -> policy epilogue (bias, activation,
+//                   pooling sums, gradient contractions ...) -> global memory
+//   warps 6..9    : (policies with kSynthA) build the A stage in shared memory themselves, in the
+//                   UMMA SWIZZLE_128B layout -- used for the interaction cube, which never exists
+//                   in HBM (CFFM.py:355-367)
+//
+// Three mbarrier pipelines: smem full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue,
+// two accumulator buffers), and the persistent unit loop every role walks in the same order.
+#pragma once
+#include "tc05.cuh"
+
+namespace cffm {
+namespace tc {
+
+constexpr int STAGES = 4;
+constexpr int MAX_BN = 256;
+constexpr int B_STAGE_BYTES_MAX = MAX_BN * BK * 2;
+constexpr int EXTRA_BYTES = 24 * 1024;
+constexpr int BASE_THREADS = 192, SYNTH_THREADS = 320;
+
+struct Ctl {
+  uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES_MAX) + sizeof(Ctl) + 64 + EXTRA_BYTES;
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
+  uint32_t c = 32;
+  while ((int)c < 2 * bn) c <<= 1;
+  return c;
+}
+
+struct Unit { int m_tile, n_tile; };
+
+// Policy interface (all __device__):
+//   static constexpr bool kSynthA
+//   int n_units() const; Unit unit(int u) const; int k_chunks() const; int bn() const  (UMMA N of this launch)
+//   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
+//   void load_b(uint8_t* sB, uint64_t* bar, Unit, int kc) const      -- TMA for the B stage
+//   uint32_t tx_bytes() const                                        -- bytes the TMA loads deliver per stage
+//   void synth_begin(Unit, uint8_t* extra, int t) const              -- kSynthA: per-unit staging (128 threads)
+//   void synth_a(uint8_t* sA, Unit, int kc, int row, const uint8_t* extra) const
+//   epilogue object: see each policy
+template <class P>
+__global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) k_tc(const __grid_constant__ P prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
+  Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_STAGE_BYTES_MAX);
+  uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + ((sizeof(Ctl) + 63) & ~size_t(63));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int BN = prm.bn();
+  const uint32_t ncols = tmem_cols_for(BN);
+  const int n_units = prm.n_units();
+  const int KC = prm.k_chunks();
+
+  if (warp == 0 && lane == 0) prm.prefetch();
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? 4 : 0)); mbar_init(&ctl->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&ctl->tmem_base, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const Unit un = prm.unit(u);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
+          if constexpr (!P::kSynthA) prm.load_a(sA + stage * A_STAGE_BYTES, &ctl->full[stage], un, kc);
+          prm.load_b(sB + stage * B_STAGE_BYTES_MAX, &ctl->full[stage], un, kc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        mbar_wait(&ctl->tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_STAGE_BYTES_MAX));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(d_tmem, da + (uint64_t)(k * (UMMA_K * 2 / 16)), db + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
+                      (kc | k) != 0);
+          umma_commit(&ctl->empty[stage]);              // frees the smem stage when these MMAs retire
+          if (kc == KC - 1) umma_commit(&ctl->tfull[buf]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        buf ^= 1; if (buf == 0) bphase ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // row inside the 128-row tile
+    typename P::Epilogue epi(prm, extra, row, warp - 2);
+    int buf = 0; uint32_t bphase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const Unit un = prm.unit(u);
+      mbar_wait(&ctl->tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+      epi.begin(un);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        epi.chunk(un, c0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tempty[buf]);   // accumulator buffer may be overwritten
+      epi.end(un);
+      buf ^= 1; if (buf == 0) bphase ^= 1;
+    }
+    epi.finish();
+  } else {
+    // ------------------------------------------------------------------ A synthesis (kSynthA only)
+    if constexpr (P::kSynthA) {
+      const int t = (warp - 6) * 32 + lane;  // row of the A stage this thread writes
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const Unit un = prm.unit(u);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        prm.synth_begin(un, extra + EXTRA_BYTES / 2, t);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra + EXTRA_BYTES / 2);
+          fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, ncols);
+}
+
+}  // namespace tc
+}  // namespace cffm

@@ -160,6 +160,14 @@ int cffm_op_sparse_adagrad_dev(float* table_dev, float* accum_dev, int32_t featu
                                const int32_t* ids_dev, const float* grads_dev, int64_t n, float lr,
                                int32_t* uniq_dev, int32_t* n_uniq_dev, void* stream);
 
+/* bf16 tensor-core GEMM used by the conv stack in CFFM_PREC_BF16 mode, exposed for validation:
+ * C[M,N] (fp32, row-major) = A[M,K] . B[N,K]^T, A and B bf16 row-major (K contiguous, K % 8 == 0).
+ * tcgen05.mma with TMA-staged operands and fp32 accumulation in TMEM. */
+int cffm_op_gemm_bf16_dev(const void* a_dev, const void* b_dev, float* c_dev, int32_t M, int32_t N, int32_t K,
+                          void* stream);
+/* message of the last failed tensor-core launch on this thread */
+const char* cffm_tc_last_error(void);
+
 /* ---- intermediate tensors of the last forward / train step, for parity tests ---------------
  * what: "out", "final2", "final", "linear", "t1", "outer_rows", "conv_<l>" (pre-activation Y_l),
  *       "grad_out", "grad_inner_rows", "grad_outer_rows", "grad_bias_rows", "dense_grads",
