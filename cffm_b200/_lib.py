@@ -123,6 +123,7 @@ def _declare(lib):
         "cffm_op_gather_dev": (C.c_int, [vp, vp, i64, i32, vp, vp]),
         "cffm_op_sparse_adagrad_dev": (C.c_int, [vp, vp, i32, i32, vp, vp, i64, f32, vp, vp, vp]),
         "cffm_op_gemm_bf16_dev": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
+        "cffm_op_gemm_bf16_tn_dev": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
         "cffm_tc_last_error": (C.c_char_p, []),
         "cffm_debug_fetch": (C.c_int, [vp, C.c_char_p, vp, i64, P(i64)]),
         "cffm_debug_dense_grad": (C.c_int, [vp, C.c_char_p, vp, i64]),

@@ -36,13 +36,16 @@ bool TmaEncoder::encode_bf16(CUtensorMap* out, void* base, int rank, const uint6
 namespace tc {
 
 // ---- plain GEMM policy ------------------------------------------------------------------------
-struct PlainGemm {
+struct PlainGemm : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN); }
+  static constexpr int kStages = 4, kExtraBytes = 0;
   CUtensorMap mapA, mapB;   // A: dims (K, M) box (64, 128); B: dims (K, N) box (64, BN)
   float* C; int M, N, K, BN, tiles_n;
   __device__ int bn() const { return BN; }
   __device__ int n_units() const { return ((M + BM - 1) / BM) * tiles_n; }
-  __device__ Unit unit(int u) const { return {u / tiles_n, u % tiles_n}; }
+  __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
+  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n}; }
   __device__ int k_chunks() const { return (K + BK - 1) / BK; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + BN * BK * 2); }
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
@@ -53,6 +56,45 @@ struct PlainGemm {
   struct Epilogue {
     const PlainGemm& p; int row;
     __device__ Epilogue(const PlainGemm& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}
+    __device__ void begin(Unit) {}
+    __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
+      const int m = un.m_tile * BM + row;
+      if (m >= p.M) return;
+      float* dst = p.C + (int64_t)m * p.N + un.n_tile * p.BN + c0;
+      const int nleft = p.N - (un.n_tile * p.BN + c0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nleft) dst[j] = v[j];
+    }
+    __device__ void end(Unit) {}
+    __device__ void finish() {}
+  };
+};
+
+// ---- TN GEMM policy: C[M,N] = sum_r A[r,M] B[r,N] (both operands MN-major) ---------------------
+struct PlainGemmTN : MNMajorA, MNMajorB {
+  static constexpr bool kSynthA = false;
+  static constexpr int kStages = 4, kExtraBytes = 0;
+  CUtensorMap mapA, mapB;   // A: dims (M, R) box (64, 64); B: dims (N, R) box (64, 64)
+  float* C; int M, N, R, BN, tiles_n;
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN, true, true); }
+  __device__ int bn() const { return BN; }
+  __device__ int n_units() const { return ((M + BM - 1) / BM) * tiles_n; }
+  __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
+  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n}; }
+  __device__ int k_chunks() const { return (R + BK - 1) / BK; }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)((BM + BN) * BK * 2); }
+  __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    for (int i = 0; i < BM / 64; ++i) tma_load_2d(s + i * 8192, &mapA, bar, un.m_tile * BM + i * 64, kc * BK);
+  }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    for (int i = 0; i < BN / 64; ++i) tma_load_2d(s + i * 8192, &mapB, bar, un.n_tile * BN + i * 64, kc * BK);
+  }
+  __device__ void synth_begin(Unit, uint8_t*, int) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct Epilogue {
+    const PlainGemmTN& p; int row;
+    __device__ Epilogue(const PlainGemmTN& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}
     __device__ void begin(Unit) {}
     __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
       const int m = un.m_tile * BM + row;
@@ -91,7 +133,7 @@ int tc_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K, cu
   }
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(k_tc<PlainGemm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_tc<PlainGemm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<PlainGemm>()) != cudaSuccess) {
       g_tc_err = "cudaFuncSetAttribute(smem) failed"; return CFFM_ERR_CUDA;
     }
     attr_done = true;
@@ -99,13 +141,49 @@ int tc_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K, cu
   const int units = ((M + BM - 1) / BM) * p.tiles_n;
   int grid = units < 148 ? units : 148;
   if (grid < 1) grid = 1;
-  k_tc<PlainGemm><<<grid, BASE_THREADS, SMEM_BYTES, s>>>(p);
+  k_tc<PlainGemm><<<grid, BASE_THREADS, smem_bytes<PlainGemm>(), s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
+  return CFFM_OK;
+}
+
+int tc_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int R, cudaStream_t s) {
+  using namespace tc;
+  if (!g_enc.init()) { g_tc_err = "cuTensorMapEncodeTiled is not available"; return CFFM_ERR_CUDA; }
+  if (M % 8 != 0 || N % 64 != 0) { g_tc_err = "TN GEMM: M % 8 == 0 and N % 64 == 0 required"; return CFFM_ERR_INVALID; }
+  PlainGemmTN p;
+  const int bn = N >= 256 ? 256 : N;
+  p.BN = bn; p.tiles_n = (N + bn - 1) / bn; p.C = C; p.M = M; p.N = N; p.R = R;
+  const uint64_t dA[2] = {(uint64_t)M, (uint64_t)R}, sA[1] = {(uint64_t)M * 2};
+  const uint64_t dB[2] = {(uint64_t)N, (uint64_t)R}, sB[1] = {(uint64_t)N * 2};
+  const uint32_t bx[2] = {64, 64};
+  if (!g_enc.encode_bf16(&p.mapA, const_cast<void*>(A), 2, dA, sA, bx) ||
+      !g_enc.encode_bf16(&p.mapB, const_cast<void*>(B), 2, dB, sB, bx)) {
+    g_tc_err = "cuTensorMapEncodeTiled failed";
+    return CFFM_ERR_CUDA;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_tc<PlainGemmTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<PlainGemmTN>()) != cudaSuccess) {
+      g_tc_err = "cudaFuncSetAttribute(smem) failed"; return CFFM_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int units = ((M + BM - 1) / BM) * p.tiles_n;
+  int grid = units < 148 ? units : 148;
+  k_tc<PlainGemmTN><<<grid, BASE_THREADS, smem_bytes<PlainGemmTN>(), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
   return CFFM_OK;
 }
 
 }  // namespace cffm
+
+extern "C" int cffm_op_gemm_bf16_tn_dev(const void* a_dev, const void* b_dev, float* c_dev, int32_t M, int32_t N, int32_t R,
+                                        void* stream) {
+  if (!a_dev || !b_dev || !c_dev || M < 1 || N < 1 || R < 1) return CFFM_ERR_INVALID;
+  return cffm::tc_gemm_bf16_tn(a_dev, b_dev, c_dev, M, N, R, (cudaStream_t)stream);
+}
 
 extern "C" int cffm_op_gemm_bf16_dev(const void* a_dev, const void* b_dev, float* c_dev, int32_t M, int32_t N, int32_t K,
                                      void* stream) {

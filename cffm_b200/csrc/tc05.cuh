@@ -109,9 +109,23 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand (the non-reduction index is the contiguous one), SWIZZLE_128B: the tile is a set
+// of [reduction rows x 64 elements] blocks (128-byte rows, exactly what a TMA box with a 64-element
+// inner extent produces).  LBO = byte stride between 64-element blocks along M/N, SBO = byte stride
+// between groups of 8 reduction rows (1024 when the rows of a block are contiguous).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32; a_mn / b_mn select MN-major operands.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {

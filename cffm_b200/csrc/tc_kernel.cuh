@@ -16,19 +16,24 @@
 namespace cffm {
 namespace tc {
 
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int B_STAGE_BYTES_MAX = MAX_BN * BK * 2;
-constexpr int EXTRA_BYTES = 24 * 1024;
 constexpr int BASE_THREADS = 192, SYNTH_THREADS = 320;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct Ctl {
-  uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
+constexpr int CTL_BYTES = (sizeof(Ctl) + 63) & ~63;
 
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES_MAX) + sizeof(Ctl) + 64 + EXTRA_BYTES;
+// dynamic shared memory of a policy: 1 KB alignment slack + stages + control block + policy scratch
+template <class P>
+constexpr size_t smem_bytes() {
+  return 1024 + (size_t)P::kStages * (A_STAGE_BYTES + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
+}
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
   uint32_t c = 32;
@@ -38,29 +43,48 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
 
 struct Unit { int m_tile, n_tile; };
 
+// Operand descriptors of one UMMA (16 reduction elements) inside a stage.
+struct KMajorA {   // rows x 64 bf16, reduction index contiguous: step = 32 bytes
+  __device__ uint64_t a_desc(uint32_t addr, int k) const { return umma_desc_k_sw128(addr) + (uint64_t)(k * 2); }
+};
+struct KMajorB {
+  __device__ uint64_t b_desc(uint32_t addr, int k) const { return umma_desc_k_sw128(addr) + (uint64_t)(k * 2); }
+};
+struct MNMajorA {  // [64 reduction rows x 64 elements] blocks of 8 KB: step = 16 rows = 2048 bytes
+  __device__ uint64_t a_desc(uint32_t addr, int k) const { return umma_desc_mn_sw128(addr + k * 2048, 8192, 1024); }
+};
+struct MNMajorB {
+  __device__ uint64_t b_desc(uint32_t addr, int k) const { return umma_desc_mn_sw128(addr + k * 2048, 8192, 1024); }
+};
+
 // Policy interface (all __device__):
 //   static constexpr bool kSynthA
-//   int n_units() const; Unit unit(int u) const; int k_chunks() const; int bn() const  (UMMA N of this launch)
+//   static constexpr int kStages, kExtraBytes (policy scratch; the second half belongs to the synth warps)
+//   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
+//   int k_chunks() const; int bn() const  (UMMA N of this launch)
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
 //   void load_b(uint8_t* sB, uint64_t* bar, Unit, int kc) const      -- TMA for the B stage
 //   uint32_t tx_bytes() const                                        -- bytes the TMA loads deliver per stage
 //   void synth_begin(Unit, uint8_t* extra, int t) const              -- kSynthA: per-unit staging (128 threads)
 //   void synth_a(uint8_t* sA, Unit, int kc, int row, const uint8_t* extra) const
+//   uint64_t a_desc(addr, k), b_desc(addr, k); uint32_t idesc()      -- UMMA descriptors (see KMajorA ...)
 //   epilogue object: see each policy
 template <class P>
 __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) k_tc(const __grid_constant__ P prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
+  constexpr int STAGES = P::kStages;
   uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
   Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_STAGE_BYTES_MAX);
-  uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + ((sizeof(Ctl) + 63) & ~size_t(63));
+  uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + CTL_BYTES;
+  uint8_t* extra_synth = extra + P::kExtraBytes / 2;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int BN = prm.bn();
   const uint32_t ncols = tmem_cols_for(BN);
-  const int n_units = prm.n_units();
+  const int n_iters = prm.n_iters((int)blockIdx.x, (int)gridDim.x);
   const int KC = prm.k_chunks();
 
   if (warp == 0 && lane == 0) prm.prefetch();
@@ -79,8 +103,8 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const Unit un = prm.unit(u);
+      for (int it = 0; it < n_iters; ++it) {
+        const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
@@ -93,21 +117,20 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = prm.idesc();
       int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&ctl->tempty[buf], bphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sB + stage * B_STAGE_BYTES_MAX));
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES_MAX);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)(k * (UMMA_K * 2 / 16)), db + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
-                      (kc | k) != 0);
+            umma_bf16(d_tmem, prm.a_desc(a_addr, k), prm.b_desc(b_addr, k), idesc, (kc | k) != 0);
           umma_commit(&ctl->empty[stage]);              // frees the smem stage when these MMAs retire
           if (kc == KC - 1) umma_commit(&ctl->tfull[buf]);  // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -121,8 +144,8 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
     const int row = q * 32 + lane;          // row inside the 128-row tile
     typename P::Epilogue epi(prm, extra, row, warp - 2);
     int buf = 0; uint32_t bphase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const Unit un = prm.unit(u);
+    for (int it = 0; it < n_iters; ++it) {
+      const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
       mbar_wait(&ctl->tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
@@ -145,14 +168,14 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
     if constexpr (P::kSynthA) {
       const int t = (warp - 6) * 32 + lane;  // row of the A stage this thread writes
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const Unit un = prm.unit(u);
+      for (int it = 0; it < n_iters; ++it) {
+        const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        prm.synth_begin(un, extra + EXTRA_BYTES / 2, t);
+        prm.synth_begin(un, extra_synth, t);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra + EXTRA_BYTES / 2);
+          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra_synth);
           fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->full[stage]);

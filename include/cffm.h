@@ -165,6 +165,10 @@ int cffm_op_sparse_adagrad_dev(float* table_dev, float* accum_dev, int32_t featu
  * tcgen05.mma with TMA-staged operands and fp32 accumulation in TMEM. */
 int cffm_op_gemm_bf16_dev(const void* a_dev, const void* b_dev, float* c_dev, int32_t M, int32_t N, int32_t K,
                           void* stream);
+/* Same pipeline with both operands transposed (MN-major UMMA descriptors), the form the conv
+ * weight gradient takes: C[M,N] = sum_r A[r,M] * B[r,N]; A [R,M], B [R,N] bf16 row-major. */
+int cffm_op_gemm_bf16_tn_dev(const void* a_dev, const void* b_dev, float* c_dev, int32_t M, int32_t N, int32_t R,
+                             void* stream);
 /* message of the last failed tensor-core launch on this thread */
 const char* cffm_tc_last_error(void);
 

@@ -44,3 +44,20 @@ def test_bf16_gemm_identity_layout(lib):
     c = _gemm(lib, a, b)
     want = b.float().t()[idx]
     assert torch.equal(c, want)
+
+
+@pytest.mark.parametrize("M,N,R", [(128, 64, 64), (256, 256, 512), (3072, 768, 4096), (192, 64, 1000), (384, 128, 77)])
+def test_bf16_gemm_tn_matches_torch(lib, M, N, R):
+    """MN-major operands (the weight-gradient form): C = A^T B with A [R,M], B [R,N]."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + R)
+    a = torch.randn(R, M, generator=g, device="cuda").to(torch.bfloat16)
+    b = torch.randn(R, N, generator=g, device="cuda").to(torch.bfloat16)
+    c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    rc = lib.cffm_op_gemm_bf16_tn_dev(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr()), M, N, R,
+                                      C.c_void_p(0))
+    assert rc == 0, lib.cffm_tc_last_error()
+    torch.cuda.synchronize()
+    want = a.float().t() @ b.float()
+    assert not torch.isnan(c).any()
+    assert (c - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
