@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcffm_b200.so")
 BUILD_DIR = os.path.join(ROOT, "build")
 
-CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu", "gemm_tc.cu"]
+CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu", "gemm_tc.cu", "conv_tc.cu"]
 CPP_SOURCES = ["libfm.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

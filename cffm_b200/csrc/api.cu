@@ -530,7 +530,18 @@ extern "C" int cffm_debug_fetch(cffm_handle* h, const char* what, float* host_ds
     const int l = atoi(w.c_str() + (grad ? 6 : 5));
     if (l < 0 || l >= m->n_live) { m->err = "no such conv layer"; return CFFM_ERR_INVALID; }
     const int64_t H = m->Ko >> (l + 1);
-    src = grad ? m->dY[l] : m->Y[l]; n = B * H * H * P;
+    n = B * H * H * P;
+    if (m->cfg.precision == CFFM_PREC_BF16) {  // bf16 mode stores X_{l+1} = phi(Y_l) (and dY_l) padded, in bf16
+      if (n_out) *n_out = n;
+      if (!host_dst || cap <= 0) return CFFM_OK;
+      float* tmp = nullptr;
+      CFFM_CUDA_OK(m, cudaMalloc((void**)&tmp, sizeof(float) * n));
+      int r = tc_debug_fetch(m, grad, l, tmp, B * H * H);
+      if (r == CFFM_OK) cudaMemcpy(host_dst, tmp, sizeof(float) * std::min(cap, n), cudaMemcpyDeviceToHost);
+      cudaFree(tmp);
+      return r;
+    }
+    src = grad ? m->dY[l] : m->Y[l];
   } else { m->err = std::string("unknown tensor: ") + what; return CFFM_ERR_INVALID; }
   if (n_out) *n_out = n;
   if ((!src && !isrc) || n == 0) { m->err = std::string("tensor not available: ") + what; return CFFM_ERR_INVALID; }

@@ -439,7 +439,7 @@ static TrainPlan make_plan(const Model* m) {
   pl.off_rows = take(m->n_small, pl.Cb);
   pl.off_Wd = m->cfg.inner_conv ? take(P * m->Ki, pl.Cb) : 0;
   pl.off_attW = m->cfg.linear_att ? take(F * F, pl.Cb) : 0;
-  for (int l = 0; l < m->n_live; ++l) {
+  for (int l = 0; l < (m->cfg.precision == CFFM_PREC_BF16 ? 0 : m->n_live); ++l) {
     const int64_t Ho = m->Ko >> (l + 1);
     const int64_t rows = B * Ho * Ho;
     const int tiles = ceil_div(4 * P, GBM) * ceil_div(P, GBN);
@@ -460,9 +460,13 @@ int model_alloc_train(Model* m) {
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   TRY(dmalloc(m, &m->gout, B));
   if (m->cfg.outer_conv) {
-    for (int l = 0; l < m->n_live; ++l) {
-      const int64_t H = m->Ko >> (l + 1);
-      TRY(dmalloc(m, &m->dY[l], B * H * H * m->P));
+    if (m->cfg.precision == CFFM_PREC_BF16) {
+      TRY(tc_alloc(m, true));
+    } else {
+      for (int l = 0; l < m->n_live; ++l) {
+        const int64_t H = m->Ko >> (l + 1);
+        TRY(dmalloc(m, &m->dY[l], B * H * H * m->P));
+      }
     }
     TRY(dmalloc(m, &m->g_outer_rows, B * F * m->Ko));
     TRY(dmalloc(m, &m->v_head, m->t1_dim));
@@ -482,7 +486,7 @@ int model_alloc_train(Model* m) {
   add(pl.off_rows, m->aux_off + m->t1_dim + 4, m->n_small, pl.Cb);
   if (m->cfg.inner_conv) add(pl.off_Wd, L.din_k, (int64_t)m->P * m->Ki, pl.Cb);
   if (m->cfg.linear_att) add(pl.off_attW, L.att_W, F * F, pl.Cb);
-  for (int l = 0; l < m->n_live; ++l) {
+  for (int l = 0; l < (m->cfg.precision == CFFM_PREC_BF16 ? 0 : m->n_live); ++l) {  // bf16: conv_tc.cu writes these
     add(pl.off_wg[l], L.conv_w[l], 4ll * m->P * m->P, pl.nsplit[l]);
     add(pl.off_bg[l], L.conv_b[l], m->P, pl.Cl[l]);
   }
@@ -553,8 +557,12 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     // offsets of the pooling levels inside t1
     int lvl_off[kMaxConv + 1]; lvl_off[0] = 0;
     for (int l = 0; l < m->conv_depth; ++l) lvl_off[l + 1] = lvl_off[l] + (K >> l);
+    if (m->cfg.precision == CFFM_PREC_BF16) {
+      int r = tc_conv_backward(m, B, s);
+      if (r != CFFM_OK) return r;
+    }
     // ---- top of the conv stack ----
-    {
+    if (m->cfg.precision != CFFM_PREC_BF16) {
       const int l = m->n_live - 1;
       const int H = K >> (l + 1);
       const int64_t total = (int64_t)B * H * H * P;
@@ -563,7 +571,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
           m->Y[l], m->gout, m->v_head + lvl_off[l + 1], H, P, total, m->dY[l]));
       m->launches++;
     }
-    for (int l = m->n_live - 1; l >= 0; --l) {
+    for (int l = (m->cfg.precision == CFFM_PREC_BF16 ? -1 : m->n_live - 1); l >= 0; --l) {
       const int Hin = K >> l, Ho = Hin >> 1;
       const int rows = B * Ho * Ho;
       launch_colsum(m, m->dY[l], rows, P, P, nullptr, part + pl.off_bg[l], pl.Cl[l], s);

@@ -1,0 +1,792 @@
+// Tensor-core (tcgen05) conv stack for CFFM_PREC_BF16: the 2x2/stride-2 conv layers of the outer
+// path (CFFM.py:373-391) as implicit GEMMs with bf16 operands and fp32 accumulation in TMEM.
+//
+//   layer 0   A operand = interaction cube (CFFM.py:355-367), synthesised by four producer warps
+//             straight into the UMMA shared-memory layout; it never exists in HBM.
+//   layer >=1 A operand = im2col view of the stored activations: non-overlapping 2x2 windows make
+//             im2col a pure re-index, expressed as a 5-D TMA box over the NHWC tensor.
+//   epilogues read the accumulator from TMEM and fuse bias + relu + activation + bf16 store +
+//             the sum-pooling row sums (forward), the pooling-gradient broadcast and activation
+//             mask (data gradient), or the contraction of the cube gradient with the embedding
+//             rows (layer-0 data gradient).
+//   weight gradients use MN-major descriptors (both operands "transposed"), split over the
+//             position axis, reduced in a fixed order.
+// Activations X_l = phi(Y_{l-1}) and gradients dY_l are bf16, NHWC with the channel (pair) axis
+// padded to a multiple of 32; master weights, optimizer state, pooling sums and all reductions
+// stay fp32.
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model.h"
+#include "tc_kernel.cuh"
+
+namespace cffm {
+namespace tc {
+
+typedef __nv_bfloat16 bf16;
+
+struct Geom {
+  int B, P, Pp, F, K;      // batch, pairs, padded pairs, fields, outer dims
+  int Ho, lgHo, Hin;       // output / input spatial size of this layer
+  int M;                   // B*Ho*Ho output positions
+  int BN, tiles_n;         // UMMA N and number of N tiles
+  __device__ __forceinline__ void pos(int m, int& b, int& h, int& w) const {
+    w = m & (Ho - 1); h = (m >> lgHo) & (Ho - 1); b = m >> (2 * lgHo);
+  }
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int ACT>
+__device__ __forceinline__ float phi_scale() { return ACT == CFFM_ACT_SELU ? kSeluScale : 1.f; }
+
+// =================================================================================================
+// Forward: Y_l = conv(X_l) + b_l ; X_{l+1} = phi(Y_l) (bf16) ; sum_pooling[l+1][b,h] = sum_{w,q} X_{l+1}
+// =================================================================================================
+template <int ACT, bool L0>
+struct ConvFwdTC : KMajorA, KMajorB {
+  static constexpr bool kSynthA = L0;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0;
+  CUtensorMap mapA, mapB;
+  Geom g;
+  const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
+  const float* rows; const int* pair_i; const int* pair_j;
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
+  __device__ int bn() const { return g.BN; }
+  __device__ int m_tiles() const { return (g.M + BM - 1) / BM; }
+  __device__ int n_iters(int cta, int ncta) const {
+    const int mt = m_tiles();
+    return (cta < mt ? (mt - cta + ncta - 1) / ncta : 0) * g.tiles_n;
+  }
+  __device__ Unit unit(int cta, int ncta, int it) const { return {cta + (it / g.tiles_n) * ncta, it % g.tiles_n, 0}; }
+  __device__ int k_chunks(Unit) const { return 4 * g.Pp / BK; }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)((L0 ? 0 : A_STAGE_BYTES) + g.BN * BK * 2); }
+  __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    const int m0 = un.m_tile * BM;
+    const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
+    const int k0 = kc * BK, dh = k0 / (2 * g.Pp), c0 = k0 - dh * 2 * g.Pp;
+    tma_load_5d(s, &mapA, bar, c0, 0, dh, h0, b0);
+  }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  // ---- layer 0: stage the sample's outer rows, then build 128 x 64 slabs of the cube ----
+  __device__ void synth_begin(Unit un, uint8_t* ex, int t) const {
+    float* o = reinterpret_cast<float*>(ex);
+    uint8_t* pi = ex + g.F * g.K * 4;
+    uint8_t* pj = pi + ((g.P + 15) & ~15);
+    const int b = (un.m_tile * BM) >> (2 * g.lgHo);
+    const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
+    for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
+    for (int e = t; e < g.P; e += 128) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
+  }
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t, const uint8_t* ex) const {
+    const float* o = reinterpret_cast<const float*>(ex);
+    const uint8_t* pi = ex + g.F * g.K * 4;
+    const uint8_t* pj = pi + ((g.P + 15) & ~15);
+    const int m = un.m_tile * BM + t;
+    const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
+    const int p0 = kc * 16;  // k = p*4 + dh*2 + dw: 16 pairs per 64-wide slab
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int p = p0 + 2 * c + hf;
+        float2 oi = make_float2(0.f, 0.f), oj = make_float2(0.f, 0.f);
+        if (p < g.P) {
+          oi = *reinterpret_cast<const float2*>(o + pi[p] * g.K + 2 * h);
+          oj = *reinterpret_cast<const float2*>(o + pj[p] * g.K + 2 * w);
+        }
+        pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
+        pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
+      }
+      *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  struct Epilogue {
+    const ConvFwdTC& p; int row; float rowsum;
+    __device__ Epilogue(const ConvFwdTC& p_, uint8_t*, int row_, int) : p(p_), row(row_), rowsum(0.f) {}
+    __device__ void begin(Unit un) { if (un.n_tile == 0) rowsum = 0.f; }
+    __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
+      const int m = un.m_tile * BM + row;
+      const int n0 = un.n_tile * p.g.BN + c0;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float y0 = v[j] + (n0 + j < p.g.P ? __ldg(p.bias + n0 + j) : 0.f);
+        const float y1 = v[j + 1] + (n0 + j + 1 < p.g.P ? __ldg(p.bias + n0 + j + 1) : 0.f);
+        const float x0 = phi_f<ACT>(y0), x1 = phi_f<ACT>(y1);
+        rowsum += x0 + x1;
+        pk[j >> 1] = pack2(x0, x1);
+      }
+      if (m < p.g.M) {
+        uint4* dst = reinterpret_cast<uint4*>(p.Xout + (int64_t)m * p.g.Pp + n0);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+      }
+    }
+    __device__ void end(Unit un) {
+      if (un.n_tile != p.g.tiles_n - 1) return;
+      const int m = un.m_tile * BM + row;
+      float s = m < p.g.M ? rowsum : 0.f;
+      for (int off = p.g.Ho >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      int b, h, w; p.g.pos(m, b, h, w);
+      if (w == 0 && m < p.g.M) p.t1[(int64_t)b * p.t1_dim + p.sp_off + h] = s;
+    }
+    __device__ void finish() {}
+  };
+};
+
+// =================================================================================================
+// Data gradient, layer l >= 1:
+//   dX_l[b,2h+dh,2w+dw,p] = sum_q dY_l[m,q] W_l[(dh,dw,p),q] + g_b v[sp_off + 2h+dh]
+//   dY_{l-1} = dX_l * phi'(Y_{l-1}); phi' follows from the sign of X_l = phi(Y_{l-1})
+// =================================================================================================
+template <int ACT>
+struct ConvDgradTC : KMajorA, KMajorB {
+  static constexpr bool kSynthA = false;
+  static constexpr int kStages = 4, kExtraBytes = 0;
+  CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
+  Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
+  const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
+  __device__ int bn() const { return g.BN; }
+  __device__ int n_units() const { return ((g.M + BM - 1) / BM) * g.tiles_n; }
+  __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
+  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / g.tiles_n, u % g.tiles_n, 0}; }
+  __device__ int k_chunks(Unit) const { return g.Pp / BK; }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + g.BN * BK * 2); }
+  __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  __device__ void synth_begin(Unit, uint8_t*, int) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct Epilogue {
+    const ConvDgradTC& p; int row; int64_t base; float dsp; bool ok;
+    __device__ Epilogue(const ConvDgradTC& p_, uint8_t*, int row_, int) : p(p_), row(row_), base(0), dsp(0.f), ok(false) {}
+    __device__ void begin(Unit un) {
+      const int m = un.m_tile * BM + row;
+      ok = m < p.g.M;
+      int b, h, w; p.g.pos(ok ? m : 0, b, h, w);
+      const int n0 = un.n_tile * p.g.BN;
+      const int tap = n0 / p.g.Pp, pb = n0 - tap * p.g.Pp;
+      const int dh = tap >> 1, dw = tap & 1;
+      base = (((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw) * p.g.Pp + pb;
+      dsp = ok ? __ldg(p.gout + b) * __ldg(p.v_head + p.sp_off + 2 * h + dh) : 0.f;
+    }
+    __device__ void chunk(Unit, int c0, const float (&v)[32]) {
+      if (!ok) return;
+      const uint4* xs = reinterpret_cast<const uint4*>(p.X + base + c0);
+      uint4* dst = reinterpret_cast<uint4*>(p.dYprev + base + c0);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 xv = __ldg(xs + q4);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = q4 * 8 + e * 2;
+          const float m0 = (xw[e] & 0x7FFFu) ? phi_scale<ACT>() : 0.f;        // X > 0  <=>  Y > 0
+          const float m1 = (xw[e] & 0x7FFF0000u) ? phi_scale<ACT>() : 0.f;
+          o[e] = pack2((v[j] + dsp) * m0, (v[j + 1] + dsp) * m1);
+        }
+        dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __device__ void end(Unit) {}
+    __device__ void finish() {}
+  };
+};
+
+// =================================================================================================
+// Data gradient, layer 0, contracted with the embedding rows.  A CTA owns whole
+// samples (two 128-row tiles x all N tiles) and accumulates d o[f][a] in shared memory:
+//   column n = p*4 + dh*2 + dw;  D = acc + g_b v[2h+dh]
+//   d o_i[2h+dh] += sum_{w,dw} D o_j[2w+dw]     (16 lanes of one h: halving butterfly)
+//   d o_j[2w+dw] += sum_{h,dh} D o_i[2h+dh]     (two h per warp: one exchange; per-warp slices)
+// Every accumulator has a single writer and a fixed order: the result is deterministic.
+// =================================================================================================
+struct Conv0DgradTC : KMajorA, KMajorB {
+  static constexpr bool kSynthA = false;
+  static constexpr int kStages = 3, kExtraBytes = 64 * 1024;
+  CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
+  Geom g;                   // Ho = 16: 256 rows per sample
+  const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
+  __device__ int bn() const { return g.BN; }
+  __device__ int per_sample() const { return 2 * g.tiles_n; }
+  __device__ int n_iters(int cta, int ncta) const { return (cta < g.B ? (g.B - cta + ncta - 1) / ncta : 0) * per_sample(); }
+  __device__ Unit unit(int cta, int ncta, int it) const {
+    const int ps = per_sample();
+    const int b = cta + (it / ps) * ncta, r = it % ps;
+    return {b * 2 + r / g.tiles_n, r % g.tiles_n, r};  // z = position inside the sample's unit sequence
+  }
+  __device__ int k_chunks(Unit) const { return g.Pp / BK; }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + g.BN * BK * 2); }
+  __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  __device__ void synth_begin(Unit, uint8_t*, int) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct Epilogue {
+    const Conv0DgradTC& p; int row, ew, lane;
+    float *o, *dOi, *dOj;   // smem: rows [F*K], d o_i [F*K], per-warp d o_j slices [4][F*K]
+    uint8_t *pi, *pj;
+    float dsp0, dsp1; int h, w;
+    __device__ Epilogue(const Conv0DgradTC& p_, uint8_t* ex, int row_, int ew_) : p(p_), row(row_), ew(ew_) {
+      const int FK = p.g.F * p.g.K;
+      lane = threadIdx.x & 31;
+      o = reinterpret_cast<float*>(ex); dOi = o + FK; dOj = dOi + FK;
+      pi = reinterpret_cast<uint8_t*>(dOj + 4 * FK); pj = pi + ((p.g.P + 15) & ~15);
+      const int t = ew * 32 + lane;
+      for (int e = t; e < p.g.P; e += 128) { pi[e] = (uint8_t)p.pair_i[e]; pj[e] = (uint8_t)p.pair_j[e]; }
+      dsp0 = dsp1 = 0.f; h = w = 0;
+    }
+    __device__ void epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+    __device__ void begin(Unit un) {
+      const int FK = p.g.F * p.g.K, t = ew * 32 + lane;
+      const int b = un.m_tile >> 1;
+      if (un.z == 0) {  // first unit of a sample: stage its rows, clear the accumulators
+        epi_sync();
+        const float* src = p.rows + (int64_t)b * FK;
+        for (int e = t; e < FK; e += 128) { o[e] = __ldg(src + e); dOi[e] = 0.f; }
+        for (int e = t; e < 4 * FK; e += 128) dOj[e] = 0.f;
+        epi_sync();
+      }
+      const int r = (un.m_tile & 1) * BM + row;   // position inside the sample
+      h = r >> 4; w = r & 15;
+      const float gb = __ldg(p.gout + b);
+      dsp0 = gb * __ldg(p.v_head + 2 * h); dsp1 = gb * __ldg(p.v_head + 2 * h + 1);
+    }
+    __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
+      const int K = p.g.K;
+      const int pbase = (un.n_tile * p.g.BN + c0) >> 2;   // 8 pairs in this 32-column chunk
+      float ci[16], cj[16];
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        const int pr = pbase + pp;
+        float2 oi = make_float2(0.f, 0.f), oj = make_float2(0.f, 0.f);
+        if (pr < p.g.P) {
+          oi = *reinterpret_cast<const float2*>(o + pi[pr] * K + 2 * h);
+          oj = *reinterpret_cast<const float2*>(o + pj[pr] * K + 2 * w);
+        }
+        const float D00 = v[4 * pp] + dsp0, D01 = v[4 * pp + 1] + dsp0, D10 = v[4 * pp + 2] + dsp1, D11 = v[4 * pp + 3] + dsp1;
+        ci[2 * pp] = fmaf(D01, oj.y, D00 * oj.x); ci[2 * pp + 1] = fmaf(D11, oj.y, D10 * oj.x);
+        cj[2 * pp] = fmaf(D10, oi.y, D00 * oi.x); cj[2 * pp + 1] = fmaf(D11, oi.y, D01 * oi.x);
+      }
+      // d o_i: reduce the 16 values over the 16 lanes (w) of this h; lane r ends with value r
+#pragma unroll
+      for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int k = 0; k < s; ++k) {
+          const float send = up ? ci[k] : ci[k + s];
+          const float keep = up ? ci[k + s] : ci[k];
+          ci[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      {  // consecutive pairs usually share their first field: one pair at a time, so an address has one writer
+        const int r = lane & 15, pr = pbase + (r >> 1);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if ((r >> 1) == pp && pr < p.g.P) dOi[pi[pr] * K + 2 * h + (r & 1)] += ci[0];
+          __syncwarp();
+        }
+      }
+      // d o_j: add the warp's two h rows (lanes l and l^16); lanes 0-15 keep pairs 0-3, 16-31 pairs 4-7
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float send = up ? cj[k] : cj[k + 8];
+          const float keep = up ? cj[k + 8] : cj[k];
+          cj[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+        float* slice = dOj + ew * p.g.F * K;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // pairs 4 apart may share their second field: halves take turns
+          if ((int)up == half) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int pr = pbase + (up ? 4 : 0) + (k >> 1);
+              if (pr < p.g.P) slice[pj[pr] * K + 2 * w + (k & 1)] += cj[k];
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __device__ void end(Unit un) {
+      if (un.z != p.per_sample() - 1) return;
+      const int FK = p.g.F * p.g.K, t = ew * 32 + lane;
+      const int b = un.m_tile >> 1;
+      epi_sync();
+      float* dst = p.g_rows + (int64_t)b * FK;
+      for (int e = t; e < FK; e += 128) dst[e] = dOi[e] + ((dOj[e] + dOj[FK + e]) + (dOj[2 * FK + e] + dOj[3 * FK + e]));
+    }
+    __device__ void finish() {}
+  };
+};
+
+// =================================================================================================
+// Weight gradient: dW_l[k, q] = sum_m A[m, k] dY_l[m, q], the position axis m split over gridDim
+// (unit.z); partial tiles land in fp32 scratch [split][4Pp][Pp] and are reduced in order afterwards.
+// B (= dY_l) is MN-major via TMA; A is MN-major via the im2col TMA box (l >= 1) or synthesised
+// K-major by the producer warps (layer 0: the cube).
+// =================================================================================================
+template <int ACT, bool L0>
+struct ConvWgradTC : KMajorA, MNMajorB {
+  static constexpr bool kSynthA = L0;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0;
+  CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
+  Geom g;                   // BN divides Pp, multiple of 64
+  int chunks_total, chunks_per_split, n_split;
+  float* partial;
+  const float* rows; const int* pair_i; const int* pair_j;
+  __device__ uint64_t a_desc(uint32_t addr, int k) const {
+    if (L0) return umma_desc_k_sw128(addr) + (uint64_t)(k * 2);
+    return umma_desc_mn_sw128(addr + k * 2048, 8192, 1024);
+  }
+  __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN, !L0, true); }
+  __device__ int bn() const { return g.BN; }
+  __device__ int m_tiles() const { return 4 * g.Pp / BM; }
+  __device__ int n_units() const { return m_tiles() * g.tiles_n * n_split; }
+  __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
+  __device__ Unit unit(int cta, int ncta, int it) const {
+    const int u = cta + it * ncta;
+    const int tiles = m_tiles() * g.tiles_n;
+    const int z = u / tiles, r = u - z * tiles;
+    return {r / g.tiles_n, r % g.tiles_n, z};
+  }
+  __device__ int k_chunks(Unit un) const {
+    const int c0 = un.z * chunks_per_split;
+    const int c1 = min(chunks_total, c0 + chunks_per_split);
+    return c1 - c0;
+  }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)((L0 ? 0 : A_STAGE_BYTES) + g.BN * BK * 2); }
+  __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    const int m0 = (un.z * chunks_per_split + kc) * BK;   // first of the 64 positions of this stage
+    const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int kk0 = (un.m_tile * 2 + i) * 64;
+      const int dh = kk0 / (2 * g.Pp), c0 = kk0 - dh * 2 * g.Pp;
+      tma_load_5d(s + i * 8192, &mapA, bar, c0, 0, dh, h0, b0);
+    }
+  }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    const int m0 = (un.z * chunks_per_split + kc) * BK;
+    for (int i = 0; i < g.BN / 64; ++i) tma_load_2d(s + i * 8192, &mapB, bar, un.n_tile * g.BN + i * 64, m0);
+  }
+  // ---- layer 0: rows of the A stage are cube channels k = p*4 + dh*2 + dw, columns 64 positions ----
+  __device__ void synth_begin(Unit, uint8_t* ex, int t) const {
+    uint8_t* pi = ex + g.F * g.K * 4;
+    uint8_t* pj = pi + ((g.P + 15) & ~15);
+    for (int e = t; e < g.P; e += 128) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
+    reinterpret_cast<int*>(pj + ((g.P + 15) & ~15))[0] = -1;  // sample whose rows are staged
+  }
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t, const uint8_t* ex_c) const {
+    uint8_t* ex = const_cast<uint8_t*>(ex_c);
+    float* o = reinterpret_cast<float*>(ex);
+    const uint8_t* pi = ex + g.F * g.K * 4;
+    const uint8_t* pj = pi + ((g.P + 15) & ~15);
+    int* staged = reinterpret_cast<int*>(const_cast<uint8_t*>(pj) + ((g.P + 15) & ~15));
+    const int m0 = (un.z * chunks_per_split + kc) * BK;   // 64 positions: 4 h-rows x 16 w of one sample
+    const int b = m0 >> 8, hb = (m0 >> 4) & 15;
+    if (*staged != b) {                                   // uniform across the 128 producer threads
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (b < g.B) {
+        const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
+        for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
+      } else {
+        for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (t == 0) *staged = b;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const int kk = un.m_tile * BM + t;
+    const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
+    const bool live = pr < g.P;
+    const float* oi = o + (live ? pi[pr] : 0) * g.K + dh;
+    const float* oj = o + (live ? pj[pr] : 0) * g.K + dw;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                         // 8 positions: h = hb + c/2, w = (c&1)*8 .. +7
+      const float a = live ? oi[2 * (hb + (c >> 1))] : 0.f;
+      const float* ojw = oj + 2 * ((c & 1) * 8);
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * ojw[4 * e], a * ojw[4 * e + 2]);
+      *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  struct Epilogue {
+    const ConvWgradTC& p; int row;
+    __device__ Epilogue(const ConvWgradTC& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}
+    __device__ void begin(Unit) {}
+    __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
+      float4* dst = reinterpret_cast<float4*>(p.partial + ((int64_t)un.z * 4 * p.g.Pp + un.m_tile * BM + row) * p.g.Pp +
+                                              un.n_tile * p.g.BN + c0);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) dst[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+    }
+    __device__ void end(Unit) {}
+    __device__ void finish() {}
+  };
+};
+
+// =================================================================================================
+// Small kernels around the GEMMs
+// =================================================================================================
+// bf16 operand copies of the fp32 master filters W_l[(tap,p), q] (HWIO, CFFM.py:376-377):
+//   Wt[q][kk] (forward B operand) and Wd[kk][q] (data-gradient B operand), zero padded, with
+//   kk = tap*Pp + p for l >= 1 and kk = p*4 + tap for layer 0 (the order the cube is synthesised in).
+__global__ void k_prep_weights(const float* __restrict__ W, int P, int Pp, int l0, bf16* __restrict__ Wt, bf16* __restrict__ Wd) {
+  const int64_t total = (int64_t)4 * Pp * Pp;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(e / Pp), q = (int)(e - (int64_t)kk * Pp);
+    int tap, pr;
+    if (l0) { pr = kk >> 2; tap = kk & 3; } else { tap = kk / Pp; pr = kk - tap * Pp; }
+    const float v = (pr < P && q < P) ? W[((int64_t)tap * P + pr) * P + q] : 0.f;
+    const bf16 b = __float2bfloat16_rn(v);
+    Wd[e] = b;
+    Wt[(int64_t)q * 4 * Pp + kk] = b;
+  }
+}
+
+// dW[(tap,p), q] = sum_split partial[split][kk][q]
+__global__ void k_wgrad_reduce(const float* __restrict__ partial, int n_split, int P, int Pp, int l0, float* __restrict__ gW) {
+  const int64_t total = (int64_t)4 * P * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / P), q = (int)(e - (int64_t)r * P);
+    const int tap = r / P, pr = r - tap * P;
+    const int kk = l0 ? pr * 4 + tap : tap * Pp + pr;
+    float s = 0.f;
+    for (int z = 0; z < n_split; ++z) s += partial[((int64_t)z * 4 * Pp + kk) * Pp + q];
+    gW[e] = s;
+  }
+}
+
+// d b_l[q] = sum_m dY_l[m, q]: chunk partials over the rows, then the chunks in order
+__global__ void k_colsum_bf16(const bf16* __restrict__ X, int64_t rows, int ld, int n, float* __restrict__ partial, int C) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int c = blockIdx.y;
+  const int64_t rpc = (rows + C - 1) / C;
+  const int64_t r0 = (int64_t)c * rpc;
+  const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
+  float s = 0.f;
+  if (col < n)
+    for (int64_t r = r0 + warp; r < r1; r += 8) s += __bfloat162float(X[r * ld + col]);
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][lane];
+    partial[(int64_t)c * n + col] = t;
+  }
+}
+__global__ void k_sum_chunks(const float* __restrict__ partial, int n, int C, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += partial[(int64_t)c * n + j];
+  out[j] = s;
+}
+
+// dY of the last live layer: X_{d-1} feeds sum_pooling[d-1] only
+template <int ACT>
+__global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restrict__ gout, const float* __restrict__ v_lvl,
+                              int H, int Pp, int64_t total, bf16* __restrict__ dY) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t pix = e / Pp;
+  const int64_t bh = pix / H;
+  const int h = (int)(bh % H);
+  const int64_t b = bh / H;
+  const float m = __bfloat162float(X[e]) > 0.f ? phi_scale<ACT>() : 0.f;
+  dY[e] = __float2bfloat16_rn(gout[b] * v_lvl[h] * m);
+}
+
+}  // namespace tc
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+using namespace tc;
+
+struct TCState {
+  int Pp = 0, BN = 0;
+  bf16* X[kMaxConv + 1] = {};    // X[l], l = 1..n_live: phi(Y_{l-1}), NHWC [B, K>>l, K>>l, Pp]
+  bf16* dY[kMaxConv] = {};       // dY[l], l = 0..n_live-1
+  bf16* Wt[kMaxConv] = {};       // [Pp][4Pp]
+  bf16* Wd[kMaxConv] = {};       // [4Pp][Pp]
+  float* wg_partial = nullptr;   // weight-gradient split scratch
+  int64_t wg_partial_floats = 0;
+  float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
+  TmaEncoder enc;
+};
+
+static int ilog2i(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
+
+static int pick_bn(int Pp) {  // largest multiple of 64 (<= 256) dividing Pp, else 32
+  for (int bn = 256; bn >= 64; bn -= 64) if (Pp % bn == 0) return bn;
+  return 32;
+}
+
+template <class T>
+static int tcmalloc(Model* m, T** p, int64_t n) {
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (size_t)(n > 0 ? n : 1));
+  if (e != cudaSuccess) { m->err = std::string("cudaMalloc (bf16 path): ") + cudaGetErrorString(e); *p = nullptr; return CFFM_ERR_NOMEM; }
+  return CFFM_OK;
+}
+#define TCTRY(x) do { int _r = (x); if (_r != CFFM_OK) return _r; } while (0)
+
+int tc_supported(Model* m) {
+  if (!m->cfg.outer_conv) return CFFM_OK;
+  if (m->Ko != 32) { m->err = "precision bf16 needs outer_dims == 32 (other sizes run in fp32)"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->cfg.activation == CFFM_ACT_GELU) { m->err = "precision bf16 does not support gelu yet (its derivative needs the pre-activation)"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->F > 48) { m->err = "precision bf16 needs num_field <= 48"; return CFFM_ERR_UNSUPPORTED; }
+  return CFFM_OK;
+}
+
+int tc_alloc(Model* m, bool train) {
+  if (!m->cfg.outer_conv) return CFFM_OK;
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  if (!st) {
+    st = new TCState();
+    m->tcs = st;
+    if (!st->enc.init()) { m->err = "cuTensorMapEncodeTiled is not available"; return CFFM_ERR_CUDA; }
+    st->Pp = (m->P + 31) & ~31;
+    st->BN = pick_bn(st->Pp);
+    const int64_t B = m->max_batch, Pp = st->Pp;
+    for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
+    for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
+  }
+  if (train && !st->dY[0]) {
+    const int64_t B = m->max_batch, Pp = st->Pp;
+    for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dY[l], B * H * H * Pp)); }
+    // split factor of the largest weight gradient decides the scratch size
+    const int tiles = (4 * st->Pp / BM) * (st->Pp / st->BN);
+    int max_split = (2 * 148 + tiles - 1) / tiles; if (max_split < 1) max_split = 1;
+    st->wg_partial_floats = (int64_t)max_split * 4 * Pp * Pp;
+    TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
+    TCTRY(tcmalloc(m, &st->bg_partial, 64 * (int64_t)m->P));
+  }
+  return CFFM_OK;
+}
+
+void tc_free(Model* m) {
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  if (!st) return;
+  for (int l = 0; l <= kMaxConv; ++l) if (st->X[l]) cudaFree(st->X[l]);
+  for (int l = 0; l < kMaxConv; ++l) { if (st->dY[l]) cudaFree(st->dY[l]); if (st->Wt[l]) cudaFree(st->Wt[l]); if (st->Wd[l]) cudaFree(st->Wd[l]); }
+  if (st->wg_partial) cudaFree(st->wg_partial);
+  if (st->bg_partial) cudaFree(st->bg_partial);
+  delete st;
+  m->tcs = nullptr;
+}
+
+static Geom make_geom(const Model* m, const TCState* st, int B, int l) {
+  Geom g;
+  g.B = B; g.P = m->P; g.Pp = st->Pp; g.F = m->F; g.K = m->Ko;
+  g.Hin = m->Ko >> l; g.Ho = g.Hin >> 1; g.lgHo = ilog2i(g.Ho);
+  g.M = B * g.Ho * g.Ho; g.BN = st->BN; g.tiles_n = st->Pp / st->BN;
+  return g;
+}
+
+// 5-D im2col view of an NHWC bf16 tensor [B, Hin, Hin, Pp]: (c = (dw,p), w, dh, h, b); box = 64 channels x `rows` positions
+static bool im2col_map(const TCState* st, CUtensorMap* map, const bf16* X, int B, int Hin, int Pp, int rows) {
+  const int Ho = Hin / 2;
+  const uint64_t dims[5] = {(uint64_t)2 * Pp, (uint64_t)Ho, 2, (uint64_t)Ho, (uint64_t)B};
+  const uint64_t str[4] = {(uint64_t)2 * Pp * 2, (uint64_t)Hin * Pp * 2, (uint64_t)2 * Hin * Pp * 2, (uint64_t)Hin * Hin * Pp * 2};
+  int bw = Ho, bh = rows / bw; if (bh > Ho) bh = Ho; if (bh < 1) bh = 1;
+  int bb = rows / (bw * bh); if (bb < 1) bb = 1;
+  const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bb};
+  return st->enc.encode_bf16(map, const_cast<bf16*>(X), 5, dims, str, box);
+}
+static bool mat_map(const TCState* st, CUtensorMap* map, const bf16* X, int64_t rows, int cols, int box_rows, int box_cols) {
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  const uint64_t str[1] = {(uint64_t)cols * 2};
+  const uint32_t box[2] = {(uint32_t)box_cols, (uint32_t)box_rows};
+  return st->enc.encode_bf16(map, const_cast<bf16*>(X), 2, dims, str, box);
+}
+
+template <class Pol>
+static int launch_tc(Model* m, const Pol& p, int units_hint, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    static_assert(smem_bytes<Pol>() <= (size_t)SMEM_LIMIT, "policy exceeds the shared memory of an SM");
+    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_tc<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<Pol>()));
+    attr_done = true;
+  }
+  int grid = units_hint < 148 ? units_hint : 148;
+  if (grid < 1) grid = 1;
+  k_tc<Pol><<<grid, Pol::kSynthA ? SYNTH_THREADS : BASE_THREADS, smem_bytes<Pol>(), s>>>(p);
+  m->launches++;
+  CFFM_CUDA_OK(m, cudaGetLastError());
+  return CFFM_OK;
+}
+#define TC_MAP_OK(m, ok) do { if (!(ok)) { (m)->err = "cuTensorMapEncodeTiled failed"; return CFFM_ERR_CUDA; } } while (0)
+
+int tc_prep_weights(Model* m, cudaStream_t s) {
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  CFFM_PROF(m, "prep_weights_bf16", s);
+  for (int l = 0; l < m->n_live; ++l) {
+    const int64_t total = 4ll * st->Pp * st->Pp;
+    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l]);
+    m->launches++;
+  }
+  CFFM_CUDA_OK(m, cudaGetLastError());
+  return CFFM_OK;
+}
+
+template <int ACT>
+static int conv_forward_act(Model* m, int B, cudaStream_t s) {
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  const int K = m->Ko, Pp = st->Pp;
+  int off = K;
+  for (int l = 0; l < m->n_live; ++l) {
+    const Geom g = make_geom(m, st, B, l);
+    const std::string tag = "conv_fwd_l" + std::to_string(l);
+    CFFM_PROF(m, tag.c_str(), s);
+    const int m_tiles = (g.M + BM - 1) / BM;
+    if (l == 0) {
+      ConvFwdTC<ACT, true> p;
+      p.g = g; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
+      p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
+      memset(&p.mapA, 0, sizeof(p.mapA));
+      TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g.BN, 64));
+      TCTRY(launch_tc(m, p, m_tiles, s));
+    } else {
+      ConvFwdTC<ACT, false> p;
+      p.g = g; p.bias = m->dense_w + m->lay.conv_b[l]; p.Xout = st->X[l + 1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
+      p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr;
+      TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
+      TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[l], Pp, 4 * Pp, g.BN, 64));
+      TCTRY(launch_tc(m, p, m_tiles, s));
+    }
+    off += g.Ho;
+  }
+  return CFFM_OK;
+}
+
+int tc_conv_forward(Model* m, int B, cudaStream_t s) {
+  int r = tc_prep_weights(m, s);
+  if (r != CFFM_OK) return r;
+  CFFM_DISPATCH_ACT(m->cfg.activation, r = conv_forward_act<ACT>(m, B, s));
+  return r;
+}
+
+template <int ACT>
+static int conv_backward_act(Model* m, int B, cudaStream_t s) {
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  const int K = m->Ko, Pp = st->Pp, P = m->P;
+  float* g = m->dense_g;
+  int lvl_off[kMaxConv + 1]; lvl_off[0] = 0;
+  for (int l = 0; l < m->conv_depth; ++l) lvl_off[l + 1] = lvl_off[l] + (K >> l);
+  {  // top of the stack
+    const int l = m->n_live - 1;
+    const int H = K >> (l + 1);
+    const int64_t total = (int64_t)B * H * H * Pp;
+    CFFM_PROF(m, "dy_top", s);
+    k_dy_top_bf16<ACT><<<ceil_div(total, 256), 256, 0, s>>>(st->X[l + 1], m->gout, m->v_head + lvl_off[l + 1], H, Pp, total, st->dY[l]);
+    m->launches++;
+  }
+  for (int l = m->n_live - 1; l >= 0; --l) {
+    const Geom gm = make_geom(m, st, B, l);
+    const int64_t rows = gm.M;
+    {  // bias gradient
+      CFFM_PROF(m, "colsum", s);
+      const int C = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));
+      dim3 grid(ceil_div(P, 32), C);
+      k_colsum_bf16<<<grid, 256, 0, s>>>(st->dY[l], rows, Pp, P, st->bg_partial, C);
+      k_sum_chunks<<<ceil_div(P, 128), 128, 0, s>>>(st->bg_partial, P, C, g + m->lay.conv_b[l]);
+      m->launches += 2;
+    }
+    {  // weight gradient
+      const std::string tag = "conv_wgrad_l" + std::to_string(l);
+      CFFM_PROF(m, tag.c_str(), s);
+      const int tiles = (4 * Pp / BM) * gm.tiles_n;
+      const int chunks_total = (int)((rows + BK - 1) / BK);
+      int want = (2 * 148 + tiles - 1) / tiles;
+      if ((int64_t)want * 4 * Pp * Pp > st->wg_partial_floats) want = (int)(st->wg_partial_floats / (4ll * Pp * Pp));
+      if (want > chunks_total) want = chunks_total;
+      if (want < 1) want = 1;
+      const int cps = (chunks_total + want - 1) / want;
+      const int n_split = (chunks_total + cps - 1) / cps;
+      if (l == 0) {
+        ConvWgradTC<ACT, true> p;
+        p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
+        p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
+        memset(&p.mapA, 0, sizeof(p.mapA));
+        TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[0], rows, Pp, 64, 64));
+        TCTRY(launch_tc(m, p, tiles * n_split, s));
+      } else {
+        ConvWgradTC<ACT, false> p;
+        p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
+        p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr;
+        TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, gm.Hin, Pp, 64));
+        TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[l], rows, Pp, 64, 64));
+        TCTRY(launch_tc(m, p, tiles * n_split, s));
+      }
+      const int64_t total = 4ll * P * P;
+      int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+      k_wgrad_reduce<<<blocks, 256, 0, s>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
+      m->launches++;
+    }
+    {  // data gradient
+      const std::string tag = "conv_dgrad_l" + std::to_string(l);
+      CFFM_PROF(m, tag.c_str(), s);
+      Geom gd = gm; gd.tiles_n = 4 * Pp / gm.BN;
+      if (l == 0) {
+        Conv0DgradTC p;
+        p.g = gd; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
+        p.g_rows = m->g_outer_rows;
+        TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[0], rows, Pp, BM, 64));
+        TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wd[0], 4 * Pp, Pp, gd.BN, 64));
+        TCTRY(launch_tc(m, p, B, s));
+      } else {
+        ConvDgradTC<ACT> p;
+        p.g = gd; p.X = st->X[l]; p.dYprev = st->dY[l - 1]; p.gout = m->gout; p.v_head = m->v_head; p.sp_off = lvl_off[l];
+        TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[l], rows, Pp, BM, 64));
+        TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wd[l], 4 * Pp, Pp, gd.BN, 64));
+        TCTRY(launch_tc(m, p, ((gd.M + BM - 1) / BM) * gd.tiles_n, s));
+      }
+    }
+  }
+  return CFFM_OK;
+}
+
+int tc_conv_backward(Model* m, int B, cudaStream_t s) {
+  int r = CFFM_OK;
+  CFFM_DISPATCH_ACT(m->cfg.activation, r = conv_backward_act<ACT>(m, B, s));
+  return r;
+}
+
+// debug access for the parity tests: X_{l+1} = phi(Y_l) converted to fp32 [B,Ho,Ho,P]
+__global__ void k_unpad_bf16(const bf16* __restrict__ X, int64_t rows, int P, int Pp, float* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * P) return;
+  const int64_t r = e / P; const int c = (int)(e - r * P);
+  out[e] = __bfloat162float(X[r * Pp + c]);
+}
+int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows) {
+  TCState* st = reinterpret_cast<TCState*>(m->tcs);
+  if (!st) return CFFM_ERR_INVALID;
+  const bf16* src = grad ? st->dY[l] : st->X[l + 1];
+  if (!src) return CFFM_ERR_INVALID;
+  k_unpad_bf16<<<ceil_div(rows * m->P, 256), 256>>>(src, rows, m->P, st->Pp, dev_out);
+  return cudaDeviceSynchronize() == cudaSuccess ? CFFM_OK : CFFM_ERR_CUDA;
+}
+
+}  // namespace cffm

@@ -45,8 +45,8 @@ struct PlainGemm : KMajorA, KMajorB {
   __device__ int bn() const { return BN; }
   __device__ int n_units() const { return ((M + BM - 1) / BM) * tiles_n; }
   __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
-  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n}; }
-  __device__ int k_chunks() const { return (K + BK - 1) / BK; }
+  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n, 0}; }
+  __device__ int k_chunks(Unit) const { return (K + BK - 1) / BK; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + BN * BK * 2); }
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
@@ -80,8 +80,8 @@ struct PlainGemmTN : MNMajorA, MNMajorB {
   __device__ int bn() const { return BN; }
   __device__ int n_units() const { return ((M + BM - 1) / BM) * tiles_n; }
   __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
-  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n}; }
-  __device__ int k_chunks() const { return (R + BK - 1) / BK; }
+  __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / tiles_n, u % tiles_n, 0}; }
+  __device__ int k_chunks(Unit) const { return (R + BK - 1) / BK; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)((BM + BN) * BK * 2); }
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {

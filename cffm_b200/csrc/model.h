@@ -118,6 +118,7 @@ struct Model {
 
   Comm* comm = nullptr;
   int world = 1, rank = 0;
+  void* tcs = nullptr;      // TCState: bf16 activations / operand copies of the tensor-core path (conv_tc.cu)
   // per-kernel CUDA-event timing (cffm_profile_enable / cffm_profile_report)
   bool prof_on = false;
   struct ProfEv { std::string tag; cudaEvent_t a, b; };
@@ -142,6 +143,14 @@ const ParamInfo* model_find(const Model* m, const char* name);
 // labels == nullptr: scoring only; otherwise loss terms and dLoss/dout are produced as well
 int run_forward(Model* m, const int32_t* ids_dev, const float* labels_dev, int64_t B, cudaStream_t s);
 int run_backward_update(Model* m, const int32_t* ids_dev, const float* labels_dev, int64_t B, cudaStream_t s);
+
+// tensor-core conv stack (CFFM_PREC_BF16), conv_tc.cu
+int tc_supported(Model* m);
+int tc_alloc(Model* m, bool train);
+void tc_free(Model* m);
+int tc_conv_forward(Model* m, int B, cudaStream_t s);
+int tc_conv_backward(Model* m, int B, cudaStream_t s);
+int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows);
 
 int comm_allreduce_f32(Model* m, float* buf, int64_t n, cudaStream_t s);
 int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s);

@@ -55,6 +55,8 @@ int model_build_layout(Model* m) {
     m->conv_depth = d; m->n_live = d - 1;
     for (int l = 0; l < d; ++l) m->t1_dim += m->Ko >> l;
   }
+  if (c.precision != CFFM_PREC_FP32 && c.precision != CFFM_PREC_BF16) { m->err = "unknown precision"; return CFFM_ERR_INVALID; }
+  if (c.precision == CFFM_PREC_BF16) { int r = tc_supported(m); if (r != CFFM_OK) return r; }
   DenseLayout& L = m->lay;
   L = DenseLayout();
   for (int i = 0; i < kMaxConv; ++i) L.conv_w[i] = L.conv_b[i] = -1;
@@ -234,9 +236,13 @@ int model_alloc(Model* m) {
   TRY(dmalloc(m, &m->ids_buf, B * F)); TRY(dmalloc(m, &m->labels_buf, B));
   if (m->cfg.outer_conv) {
     TRY(dmalloc(m, &m->outer_rows, B * F * m->Ko));
-    for (int l = 0; l < m->n_live; ++l) {
-      int64_t H = m->Ko >> (l + 1);
-      TRY(dmalloc(m, &m->Y[l], B * H * H * P));
+    if (m->cfg.precision == CFFM_PREC_BF16) {
+      TRY(tc_alloc(m, false));
+    } else {
+      for (int l = 0; l < m->n_live; ++l) {
+        int64_t H = m->Ko >> (l + 1);
+        TRY(dmalloc(m, &m->Y[l], B * H * H * P));
+      }
     }
     TRY(dmalloc(m, &m->t1, B * m->t1_dim)); TRY(dmalloc(m, &m->hid, B * 32));
   }
@@ -267,6 +273,7 @@ void model_free(Model* m) {
                  m->partials, m->fb_buf, m->all_ids, m->all_g_inner, m->all_g_outer, m->all_g_bias, m->reduce_descs,
                  m->eval_acc};
   sparse_work_free(&m->sw);
+  tc_free(m);
   for (void* p : dev) if (p) cudaFree(p);
   for (int l = 0; l < kMaxConv; ++l) { if (m->Y[l]) cudaFree(m->Y[l]); if (m->dY[l]) cudaFree(m->dY[l]); }
   for (int s = 0; s < 2; ++s) {

@@ -41,7 +41,7 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
   return c;
 }
 
-struct Unit { int m_tile, n_tile; };
+struct Unit { int m_tile, n_tile, z; };
 
 // Operand descriptors of one UMMA (16 reduction elements) inside a stage.
 struct KMajorA {   // rows x 64 bf16, reduction index contiguous: step = 32 bytes
@@ -61,7 +61,7 @@ struct MNMajorB {
 //   static constexpr bool kSynthA
 //   static constexpr int kStages, kExtraBytes (policy scratch; the second half belongs to the synth warps)
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
-//   int k_chunks() const; int bn() const  (UMMA N of this launch)
+//   int k_chunks(Unit) const (>= 1); int bn() const  (UMMA N of this launch)
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
 //   void load_b(uint8_t* sB, uint64_t* bar, Unit, int kc) const      -- TMA for the B stage
 //   uint32_t tx_bytes() const                                        -- bytes the TMA loads deliver per stage
@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   const int BN = prm.bn();
   const uint32_t ncols = tmem_cols_for(BN);
   const int n_iters = prm.n_iters((int)blockIdx.x, (int)gridDim.x);
-  const int KC = prm.k_chunks();
 
   if (warp == 0 && lane == 0) prm.prefetch();
   if (warp == 1 && lane == 0) {
@@ -105,6 +104,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
+        const int KC = prm.k_chunks(un);
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       const uint32_t idesc = prm.idesc();
       int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
       for (int it = 0; it < n_iters; ++it) {
+        const int KC = prm.k_chunks(prm.unit((int)blockIdx.x, (int)gridDim.x, it));
         mbar_wait(&ctl->tempty[buf], bphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
+        const int KC = prm.k_chunks(un);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         prm.synth_begin(un, extra_synth, t);
         asm volatile("bar.sync 1, 128;" ::: "memory");

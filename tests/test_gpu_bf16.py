@@ -1,0 +1,114 @@
+"""Parity of the tensor-core (bf16 operands, fp32 accumulation) conv stack against the fp64 oracle.
+Tolerance from BASELINE.json's north star: forward logits within 1e-2 relative in bf16 mode;
+gradients are compared at 4e-2 relative to each tensor's scale (three bf16 roundings per product)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# name: F, M, B, activation
+SHAPES = {
+    "frappe_like": (10, 400, 24, "selu"),      # P=45 -> 64 channels, one N tile of 64
+    "bx_like": (6, 300, 40, "relu"),           # P=15 -> 32
+    "mltag_like": (3, 200, 64, "elu"),         # P=3  -> 32 (mostly padding)
+    "criteo_like": (39, 2000, 6, "relu"),      # P=741 -> 768 channels, three N tiles of 256
+    "odd_batch": (12, 500, 7, "prelu"),        # P=66 -> 96, BN=32; partial M tiles everywhere
+}
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64).reshape(-1); b = np.asarray(b, np.float64).reshape(-1)
+    return float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+
+
+def _pair(name, seed=3):
+    from cffm_b200 import Engine
+    from oracle.cffm_ref import CFFMRef
+    F, M, B, act = SHAPES[name]
+    eng = Engine(M, F, 32, 32, activation=act, max_batch=B, precision="bf16", seed=seed)
+    rng = np.random.default_rng(seed)
+    eng.set_param("feature_bias", rng.normal(0, 0.05, (M, 1)).astype(np.float32))
+    eng.set_param("outer_embeddings", rng.normal(0, 0.3, (M, 32)).astype(np.float32))
+    P = F * (F - 1) // 2
+    for l in range(5):  # keep the activations O(1) through four layers: filters ~ N(0, 1/(4P))
+        eng.set_param("outer_layer_conv_weight_%d" % l, rng.normal(0, 1.0 / np.sqrt(4 * P), (2, 2, P, P)).astype(np.float32))
+    ref = CFFMRef(M, F, 32, 32, activation=act, dtype=torch.float64)
+    for k, v in eng.get_weights().items():
+        ref.params[k] = torch.from_numpy(v.astype(np.float64)).reshape(ref.params[k].shape)
+    ids = rng.integers(0, M, (B, F)).astype(np.int32)
+    ids[-1] = ids[0]
+    y = rng.choice([-1.0, 1.0], B).astype(np.float32)
+    return eng, ref, ids, y
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_bf16_forward(name):
+    eng, ref, ids, y = _pair(name)
+    out = eng.forward(ids)
+    want, inter = ref.forward(ids, return_intermediates=True)
+    B = ids.shape[0]
+    for l in range(4):  # stored activations X_{l+1} = phi(Y_l)
+        got = eng.fetch("conv_%d" % l)
+        assert _rel(got, inter["conv_%d" % l].numpy()) < 2e-2, (name, l, _rel(got, inter["conv_%d" % l].numpy()))
+    assert _rel(eng.fetch("t1").reshape(B, -1), inter["t1"].numpy()) < 1e-2
+    assert _rel(eng.fetch("final"), inter["final"].numpy()) < 1e-2
+    assert _rel(out, want.numpy()) < 1e-2, (name, _rel(out, want.numpy()))
+    eng.close()
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_bf16_gradients(name):
+    eng, ref, ids, y = _pair(name)
+    l_ref, dense, sparse = ref.gradients(ids, y)
+    loss = eng.train_step(ids, y)
+    assert abs(loss - float(l_ref)) < 1e-2 * max(1.0, float(l_ref))
+    for l in range(4):
+        e = _rel(eng.dense_grad("outer_layer_conv_weight_%d" % l), dense["outer_layer_conv_weight_%d" % l].numpy())
+        assert e < 4e-2, (name, "wgrad", l, e)
+        e = _rel(eng.dense_grad("outer_layer_conv_bias_%d" % l), dense["outer_layer_conv_bias_%d" % l].numpy())
+        assert e < 4e-2, (name, "bgrad", l, e)
+    e = _rel(eng.fetch("grad_outer_rows"), sparse["outer_embeddings"][2].numpy())
+    assert e < 4e-2, (name, "outer rows", e)
+    # the parts that stay fp32 keep their fp32 tolerance scale (they only see the bf16 logits through the loss)
+    assert _rel(eng.fetch("grad_inner_rows"), sparse["inner_embeddings"][2].numpy()) < 2e-2
+    assert _rel(eng.dense_grad("dense_1/kernel"), dense["dense_1/kernel"].numpy()) < 2e-2
+    eng.close()
+
+
+def test_bf16_is_deterministic():
+    a, _, ids, y = _pair("frappe_like")
+    b, _, _, _ = _pair("frappe_like")
+    la = [a.train_step(ids, y) for _ in range(3)]
+    lb = [b.train_step(ids, y) for _ in range(3)]
+    assert la == lb
+    wa, wb = a.get_weights(), b.get_weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+    a.close(); b.close()
+
+
+def test_bf16_training_tracks_fp32():
+    """A short training run on the Frappe fixture: bf16 and fp32 modes end within 0.002 RMSE."""
+    import os
+    from cffm_b200 import Engine, LoadData
+    from conftest import GOLDEN
+    d = LoadData(os.path.join(GOLDEN, "frappe_mini") + "/", "frappe", "square_loss")
+    X, Y = np.array(d.Train_data["X"]), np.array(d.Train_data["Y"])
+    Xv, Yv = np.array(d.Validation_data["X"]), np.array(d.Validation_data["Y"])
+    res = {}
+    for prec in ("fp32", "bf16"):
+        eng = Engine(d.features_M, 10, 32, 32, activation="selu", max_batch=256, precision=prec, seed=11)
+        for ep in range(6):
+            for s in range(0, 3000 - 255, 256):
+                eng.train_step(X[s:s + 256], Y[s:s + 256])
+        res[prec] = eng.evaluate(Xv, Yv, 256)[0]
+        eng.close()
+    assert abs(res["fp32"] - res["bf16"]) < 2e-3 + 0.02 * res["fp32"], res
+
+
+def test_bf16_rejects_what_it_cannot_do():
+    from cffm_b200 import Engine, CffmError
+    with pytest.raises(CffmError):
+        Engine(100, 4, 16, 16, max_batch=4, precision="bf16")
+    with pytest.raises(CffmError):
+        Engine(100, 4, 32, 32, max_batch=4, precision="bf16", activation="gelu")
