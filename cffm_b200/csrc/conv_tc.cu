@@ -12,7 +12,7 @@
 //   weight gradients use MN-major descriptors (both operands "transposed"), split over the
 //             position axis, reduced in a fixed order.
 // Activations X_l = phi(Y_{l-1}) and gradients dY_l are bf16, NHWC with the channel (pair) axis
-// padded to a multiple of 32; master weights, optimizer state, pooling sums and all reductions
+// padded to a multiple of 64; master weights, optimizer state, pooling sums and all reductions
 // stay fp32.
 #include <stdio.h>
 
@@ -537,9 +537,9 @@ struct TCState {
 
 static int ilog2i(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
 
-static int pick_bn(int Pp) {  // largest multiple of 64 (<= 256) dividing Pp, else 32
-  for (int bn = 256; bn >= 64; bn -= 64) if (Pp % bn == 0) return bn;
-  return 32;
+static int pick_bn(int Pp) {  // largest multiple of 64 (<= 256) dividing Pp
+  for (int bn = 256; bn > 64; bn -= 64) if (Pp % bn == 0) return bn;
+  return 64;
 }
 
 template <class T>
@@ -565,7 +565,7 @@ int tc_alloc(Model* m, bool train) {
     st = new TCState();
     m->tcs = st;
     if (!st->enc.init()) { m->err = "cuTensorMapEncodeTiled is not available"; return CFFM_ERR_CUDA; }
-    st->Pp = (m->P + 31) & ~31;
+    st->Pp = (m->P + 63) & ~63;   // one 64-element swizzle atom is the unit of every operand box
     st->BN = pick_bn(st->Pp);
     const int64_t B = m->max_batch, Pp = st->Pp;
     for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
