@@ -91,20 +91,27 @@ struct ConvFwdTC : KMajorA, KMajorB {
     const uint8_t* pj = pi + ((g.P + 15) & ~15);
     const int m = un.m_tile * BM + t;
     const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
-    const int p0 = kc * 16;  // k = p*4 + dh*2 + dw: 16 pairs per 64-wide slab
+    // k = p*4 + dh*2 + dw: 16 consecutive pairs per 64-wide slab.  The pair index is uniform over the
+    // CTA, so (i, j) is walked with scalar arithmetic and o_i is re-read only when i changes.
+    int p = kc * 16;
+    int i = p < g.P ? pi[p] : 0, j = p < g.P ? pj[p] : 1;
+    const float* oiw = o + 2 * h;
+    const float* ojw = o + 2 * w;
+    float2 oi = *reinterpret_cast<const float2*>(oiw + i * g.K);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       uint32_t pk[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int p = p0 + 2 * c + hf;
-        float2 oi = make_float2(0.f, 0.f), oj = make_float2(0.f, 0.f);
         if (p < g.P) {
-          oi = *reinterpret_cast<const float2*>(o + pi[p] * g.K + 2 * h);
-          oj = *reinterpret_cast<const float2*>(o + pj[p] * g.K + 2 * w);
+          const float2 oj = *reinterpret_cast<const float2*>(ojw + j * g.K);
+          pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
+          pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
+        } else {
+          pk[hf * 2 + 0] = 0u; pk[hf * 2 + 1] = 0u;
         }
-        pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
-        pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
+        ++p;
+        if (++j == g.F) { ++i; j = i + 1; if (i < g.F - 1) oi = *reinterpret_cast<const float2*>(oiw + i * g.K); }
       }
       *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -264,9 +271,59 @@ struct Conv0DgradTC : KMajorA, KMajorB {
       const float gb = __ldg(p.gout + b);
       dsp0 = gb * __ldg(p.v_head + 2 * h); dsp1 = gb * __ldg(p.v_head + 2 * h + 1);
     }
+    // 8 pairs per 32-column chunk.  Pairs are enumerated i-major (CFFM.py:304-305), so a chunk almost
+    // always covers at most two runs of equal first field: the d o_i terms of a run are summed in
+    // registers before one 16-lane reduction, and every shared-memory update below has exactly one
+    // lane per address per instruction (adds to one address come from one lane, in program order).
     __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
+      const int K = p.g.K, F = p.g.F;
+      const int pbase = (un.n_tile * p.g.BN + c0) >> 2;
+      if (pbase >= p.g.P) return;                          // padding channels only (warp-uniform)
+      const int i0 = pi[pbase], j0 = pj[pbase];
+      const int n0 = min(8, F - j0);                       // pairs of the first run inside this chunk
+      const int i1 = i0 + 1;
+      const int n1 = n0 < 8 ? min(8 - n0, F - 1 - i1) : 0;
+      if (pbase + 8 > p.g.P || n0 + n1 < 8) { chunk_generic(pbase, v); return; }
+      const float2 oiA = *reinterpret_cast<const float2*>(o + i0 * K + 2 * h);
+      const float2 oiB = *reinterpret_cast<const float2*>(o + (n1 ? i1 : i0) * K + 2 * h);
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};                  // run A dh0, run A dh1, run B dh0, run B dh1
+      float cj[16];
+      const bool up = (lane & 16) != 0;
+      float* slice = dOj + ew * F * K + 2 * w + (up ? 1 : 0);
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        const bool inA = pp < n0;
+        const int j = inA ? j0 + pp : i1 + 1 + (pp - n0);
+        const float2 oi = inA ? oiA : oiB;
+        const float2 oj = *reinterpret_cast<const float2*>(o + j * K + 2 * w);
+        const float D00 = v[4 * pp] + dsp0, D01 = v[4 * pp + 1] + dsp0, D10 = v[4 * pp + 2] + dsp1, D11 = v[4 * pp + 3] + dsp1;
+        const float c0v = fmaf(D01, oj.y, D00 * oj.x), c1v = fmaf(D11, oj.y, D10 * oj.x);
+        if (inA) { s4[0] += c0v; s4[1] += c1v; } else { s4[2] += c0v; s4[3] += c1v; }
+        cj[2 * pp] = fmaf(D10, oi.y, D00 * oi.x); cj[2 * pp + 1] = fmaf(D11, oi.y, D01 * oi.x);
+      }
+      // d o_i: 4 values over the 16 lanes of this h: two halving steps (lane bits 3, 2 pick the value), two plain ones
+      {
+        const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+        float x0 = (b3 ? s4[2] : s4[0]) + __shfl_xor_sync(0xffffffffu, b3 ? s4[0] : s4[2], 8);
+        float x1 = (b3 ? s4[3] : s4[1]) + __shfl_xor_sync(0xffffffffu, b3 ? s4[1] : s4[3], 8);
+        float x = (b2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, b2 ? x0 : x1, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        if ((lane & 3) == 0 && (!b3 || n1)) atomicAdd(dOi + (b3 ? i1 : i0) * K + 2 * h + (b2 ? 1 : 0), x);
+      }
+      // d o_j: the warp's two h rows are lanes l and l^16; the lower half keeps dw = 0, the upper dw = 1
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        const float send = up ? cj[2 * pp] : cj[2 * pp + 1];
+        const float keep = up ? cj[2 * pp + 1] : cj[2 * pp];
+        const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        const int j = pp < n0 ? j0 + pp : i1 + 1 + (pp - n0);
+        atomicAdd(slice + j * K, tot);
+      }
+    }
+    // Generic path: any mix of pairs (run boundaries, padding); serialised shared-memory updates.
+    __device__ void chunk_generic(int pbase, const float (&v)[32]) {
       const int K = p.g.K;
-      const int pbase = (un.n_tile * p.g.BN + c0) >> 2;   // 8 pairs in this 32-column chunk
       float ci[16], cj[16];
 #pragma unroll
       for (int pp = 0; pp < 8; ++pp) {
@@ -387,7 +444,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   }
   // ---- layer 0: rows of the A stage are cube channels k = p*4 + dh*2 + dw, columns 64 positions ----
   __device__ void synth_begin(Unit, uint8_t* ex, int t) const {
-    uint8_t* pi = ex + g.F * g.K * 4;
+    uint8_t* pi = ex + g.F * (g.K + 4) * 4;
     uint8_t* pj = pi + ((g.P + 15) & ~15);
     for (int e = t; e < g.P; e += 128) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
     reinterpret_cast<int*>(pj + ((g.P + 15) & ~15))[0] = -1;  // sample whose rows are staged
@@ -395,18 +452,19 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t, const uint8_t* ex_c) const {
     uint8_t* ex = const_cast<uint8_t*>(ex_c);
     float* o = reinterpret_cast<float*>(ex);
-    const uint8_t* pi = ex + g.F * g.K * 4;
+    const uint8_t* pi = ex + g.F * (g.K + 4) * 4;
     const uint8_t* pj = pi + ((g.P + 15) & ~15);
     int* staged = reinterpret_cast<int*>(const_cast<uint8_t*>(pj) + ((g.P + 15) & ~15));
     const int m0 = (un.z * chunks_per_split + kc) * BK;   // 64 positions: 4 h-rows x 16 w of one sample
     const int b = m0 >> 8, hb = (m0 >> 4) & 15;
+    const int KS = g.K + 4;                               // padded row stride: rows of different fields hit different banks
     if (*staged != b) {                                   // uniform across the 128 producer threads
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (b < g.B) {
-        const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
-        for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
-      } else {
-        for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int K4 = g.K / 4;
+      const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
+      for (int e = t; e < g.F * K4; e += 128) {
+        const int f = e / K4, c4 = e - f * K4;
+        reinterpret_cast<float4*>(o + f * KS)[c4] = b < g.B ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (t == 0) *staged = b;
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -414,8 +472,8 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     const int kk = un.m_tile * BM + t;
     const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
     const bool live = pr < g.P;
-    const float* oi = o + (live ? pi[pr] : 0) * g.K + dh;
-    const float* oj = o + (live ? pj[pr] : 0) * g.K + dw;
+    const float* oi = o + (live ? pi[pr] : 0) * KS + dh;
+    const float* oj = o + (live ? pj[pr] : 0) * KS + dw;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {                         // 8 positions: h = hb + c/2, w = (c&1)*8 .. +7
       const float a = live ? oi[2 * (hb + (c >> 1))] : 0.f;
