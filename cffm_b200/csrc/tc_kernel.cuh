@@ -72,7 +72,9 @@ struct MNMajorB {
 template <class P>
 __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) k_tc(const __grid_constant__ P prm) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array (an integer round trip would make
+  // every access below a generic LD/ST instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   constexpr int STAGES = P::kStages;
   uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
