@@ -82,24 +82,26 @@ struct ConvFwdTC : KMajorA, KMajorB {
     uint8_t* pj = pi + ((g.P + 15) & ~15);
     const int b = (un.m_tile * BM) >> (2 * g.lgHo);
     const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
-    for (int e = t; e < g.F * g.K / 4; e += 128) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
-    for (int e = t; e < g.P; e += 128) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
+    for (int e = t; e < g.F * g.K / 4; e += 256) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
+    for (int e = t; e < g.P; e += 256) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t, const uint8_t* ex) const {
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex) const {
     const float* o = reinterpret_cast<const float*>(ex);
     const uint8_t* pi = ex + g.F * g.K * 4;
     const uint8_t* pj = pi + ((g.P + 15) & ~15);
+    const int t = t256 & 127, half = t256 >> 7;   // row of the stage; which 4 of its 8 16-byte chunks
     const int m = un.m_tile * BM + t;
     const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
     // k = p*4 + dh*2 + dw: 16 consecutive pairs per 64-wide slab.  The pair index is uniform over the
     // CTA, so (i, j) is walked with scalar arithmetic and o_i is re-read only when i changes.
-    int p = kc * 16;
+    int p = kc * 16 + half * 8;
     int i = p < g.P ? pi[p] : 0, j = p < g.P ? pj[p] : 1;
     const float* oiw = o + 2 * h;
     const float* ojw = o + 2 * w;
     float2 oi = *reinterpret_cast<const float2*>(oiw + i * g.K);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const int c = half * 4 + c4;
       uint32_t pk[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -446,11 +448,12 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   __device__ void synth_begin(Unit, uint8_t* ex, int t) const {
     uint8_t* pi = ex + g.F * (g.K + 4) * 4;
     uint8_t* pj = pi + ((g.P + 15) & ~15);
-    for (int e = t; e < g.P; e += 128) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
+    for (int e = t; e < g.P; e += 256) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
     reinterpret_cast<int*>(pj + ((g.P + 15) & ~15))[0] = -1;  // sample whose rows are staged
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t, const uint8_t* ex_c) const {
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex_c) const {
     uint8_t* ex = const_cast<uint8_t*>(ex_c);
+    const int t = t256 & 127, half = t256 >> 7;
     float* o = reinterpret_cast<float*>(ex);
     const uint8_t* pi = ex + g.F * (g.K + 4) * 4;
     const uint8_t* pj = pi + ((g.P + 15) & ~15);
@@ -458,29 +461,32 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     const int m0 = (un.z * chunks_per_split + kc) * BK;   // 64 positions: 4 h-rows x 16 w of one sample
     const int b = m0 >> 8, hb = (m0 >> 4) & 15;
     const int KS = g.K + 4;                               // padded row stride: rows of different fields hit different banks
-    if (*staged != b) {                                   // uniform across the 128 producer threads
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (*staged != b) {                                   // uniform across the 256 producer threads
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int K4 = g.K / 4;
       const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
-      for (int e = t; e < g.F * K4; e += 128) {
+      for (int e = t256; e < g.F * K4; e += 256) {
         const int f = e / K4, c4 = e - f * K4;
         reinterpret_cast<float4*>(o + f * KS)[c4] = b < g.B ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (t == 0) *staged = b;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t256 == 0) *staged = b;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const int kk = un.m_tile * BM + t;
     const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
     const bool live = pr < g.P;
     const float* oi = o + (live ? pi[pr] : 0) * KS + dh;
-    const float* oj = o + (live ? pj[pr] : 0) * KS + dw;
+    const float4* oj4 = reinterpret_cast<const float4*>(o + (live ? pj[pr] : 0) * KS);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {                         // 8 positions: h = hb + c/2, w = (c&1)*8 .. +7
+    for (int c4 = 0; c4 < 4; ++c4) {                      // chunk c: 8 positions, h = hb + c/2, w = (c&1)*8 .. +7
+      const int c = half * 4 + c4;
       const float a = live ? oi[2 * (hb + (c >> 1))] : 0.f;
-      const float* ojw = oj + 2 * ((c & 1) * 8);
       uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * ojw[4 * e], a * ojw[4 * e + 2]);
+      for (int e = 0; e < 4; ++e) {                       // o_j[2w+dw] for two positions per 16-byte load
+        const float4 q = oj4[(c & 1) * 4 + e];
+        pk[e] = dw ? pack2(a * q.y, a * q.w) : pack2(a * q.x, a * q.z);
+      }
       *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }

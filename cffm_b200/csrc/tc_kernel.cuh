@@ -4,7 +4,7 @@
 //   warp 1        : MMA issuer (lane 0): tcgen05.mma over the stages, accumulators in TMEM
 //   warps 2..5    : epilogue: tcgen05.ld TMEM -> registers -> policy epilogue (bias, activation,
 //                   pooling sums, gradient contractions ...) -> global memory
-//   warps 6..9    : (policies with kSynthA) build the A stage in shared memory themselves, in the
+//   warps 6..13   : (policies with kSynthA) build the A stage in shared memory themselves, in the
 //                   UMMA SWIZZLE_128B layout -- used for the interaction cube, which never exists
 //                   in HBM (CFFM.py:355-367)
 //
@@ -19,7 +19,7 @@ namespace tc {
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int B_STAGE_BYTES_MAX = MAX_BN * BK * 2;
-constexpr int BASE_THREADS = 192, SYNTH_THREADS = 320;
+constexpr int BASE_THREADS = 192, SYNTH_WARPS = 8, SYNTH_THREADS = BASE_THREADS + 32 * SYNTH_WARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct Ctl {
@@ -65,7 +65,7 @@ struct MNMajorB {
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
 //   void load_b(uint8_t* sB, uint64_t* bar, Unit, int kc) const      -- TMA for the B stage
 //   uint32_t tx_bytes() const                                        -- bytes the TMA loads deliver per stage
-//   void synth_begin(Unit, uint8_t* extra, int t) const              -- kSynthA: per-unit staging (128 threads)
+//   void synth_begin(Unit, uint8_t* extra, int t) const              -- kSynthA: per-unit staging (256 threads)
 //   void synth_a(uint8_t* sA, Unit, int kc, int row, const uint8_t* extra) const
 //   uint64_t a_desc(addr, k), b_desc(addr, k); uint32_t idesc()      -- UMMA descriptors (see KMajorA ...)
 //   epilogue object: see each policy
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
 
   if (warp == 0 && lane == 0) prm.prefetch();
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? 4 : 0)); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? SYNTH_WARPS : 0)); mbar_init(&ctl->empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], 4); }
     fence_barrier_init();
   }
@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   } else {
     // ------------------------------------------------------------------ A synthesis (kSynthA only)
     if constexpr (P::kSynthA) {
-      const int t = (warp - 6) * 32 + lane;  // row of the A stage this thread writes
+      const int t = (warp - 6) * 32 + lane;  // 256 producer threads: row t & 127, half (t >> 7) of the stage row
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
         const int KC = prm.k_chunks(un);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         prm.synth_begin(un, extra_synth, t);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra_synth);
