@@ -76,46 +76,44 @@ struct ConvFwdTC : KMajorA, KMajorB {
   }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
   // ---- layer 0: stage the sample's outer rows, then build 128 x 64 slabs of the cube ----
-  __device__ void synth_begin(Unit un, uint8_t* ex, int t) const {
+  // Shared scratch of the producers: rows o[F+1][K] (row F = zeros, the target of padded pairs) and a
+  // table with one entry per pair of every stage: byte offsets of rows i and j (lo / hi 16 bits).
+  // k = p*4 + dh*2 + dw: 16 consecutive pairs per 64-wide slab; no branches in the inner loop.
+  struct SynthState {};
+  __device__ void synth_begin(Unit un, uint8_t* ex, int t, SynthState&) const {
     float* o = reinterpret_cast<float*>(ex);
-    uint8_t* pi = ex + g.F * g.K * 4;
-    uint8_t* pj = pi + ((g.P + 15) & ~15);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(ex + (g.F + 1) * g.K * 4);
     const int b = (un.m_tile * BM) >> (2 * g.lgHo);
     const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
     for (int e = t; e < g.F * g.K / 4; e += 256) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
-    for (int e = t; e < g.P; e += 256) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
+    for (int e = t; e < g.K / 4; e += 256) reinterpret_cast<float4*>(o + g.F * g.K)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t zero_row = (uint32_t)(g.F * g.K * 4);
+    for (int e = t; e < g.Pp; e += 256)
+      tab[e] = e < g.P ? ((uint32_t)(pair_i[e] * g.K * 4) | ((uint32_t)(pair_j[e] * g.K * 4) << 16)) : (zero_row | (zero_row << 16));
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex) const {
-    const float* o = reinterpret_cast<const float*>(ex);
-    const uint8_t* pi = ex + g.F * g.K * 4;
-    const uint8_t* pj = pi + ((g.P + 15) & ~15);
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex, SynthState&) const {
+    const uint8_t* o = ex;
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(ex + (g.F + 1) * g.K * 4);
     const int t = t256 & 127, half = t256 >> 7;   // row of the stage; which 4 of its 8 16-byte chunks
     const int m = un.m_tile * BM + t;
     const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
-    // k = p*4 + dh*2 + dw: 16 consecutive pairs per 64-wide slab.  The pair index is uniform over the
-    // CTA, so (i, j) is walked with scalar arithmetic and o_i is re-read only when i changes.
-    int p = kc * 16 + half * 8;
-    int i = p < g.P ? pi[p] : 0, j = p < g.P ? pj[p] : 1;
-    const float* oiw = o + 2 * h;
-    const float* ojw = o + 2 * w;
-    float2 oi = *reinterpret_cast<const float2*>(oiw + i * g.K);
+    const uint8_t* oh = o + 8 * h;
+    const uint8_t* ow = o + 8 * w;
+    const uint4* te = reinterpret_cast<const uint4*>(tab + kc * 16 + half * 8);
+    const uint4 e0 = te[0], e1 = te[1];
+    const uint32_t ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-      const int c = half * 4 + c4;
       uint32_t pk[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        if (p < g.P) {
-          const float2 oj = *reinterpret_cast<const float2*>(ojw + j * g.K);
-          pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
-          pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
-        } else {
-          pk[hf * 2 + 0] = 0u; pk[hf * 2 + 1] = 0u;
-        }
-        ++p;
-        if (++j == g.F) { ++i; j = i + 1; if (i < g.F - 1) oi = *reinterpret_cast<const float2*>(oiw + i * g.K); }
+        const uint32_t en = ent[c4 * 2 + hf];
+        const float2 oi = *reinterpret_cast<const float2*>(oh + (en & 0xFFFFu));
+        const float2 oj = *reinterpret_cast<const float2*>(ow + (en >> 16));
+        pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
+        pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
       }
-      *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(sA + sw128_offset(t, half * 4 + c4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   struct Epilogue {
@@ -174,8 +172,9 @@ struct ConvDgradTC : KMajorA, KMajorB {
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
-  __device__ void synth_begin(Unit, uint8_t*, int) const {}
-  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct SynthState {};
+  __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
     const ConvDgradTC& p; int row; int64_t base; float dsp; bool ok;
     __device__ Epilogue(const ConvDgradTC& p_, uint8_t*, int row_, int) : p(p_), row(row_), base(0), dsp(0.f), ok(false) {}
@@ -241,8 +240,9 @@ struct Conv0DgradTC : KMajorA, KMajorB {
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
-  __device__ void synth_begin(Unit, uint8_t*, int) const {}
-  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct SynthState {};
+  __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
     const Conv0DgradTC& p; int row, ew, lane;
     float *o, *dOi, *dOj;   // smem: rows [F*K], d o_i [F*K], per-warp d o_j slices [4][F*K]
@@ -445,22 +445,30 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     for (int i = 0; i < g.BN / 64; ++i) tma_load_2d(s + i * 8192, &mapB, bar, un.n_tile * g.BN + i * 64, m0);
   }
   // ---- layer 0: rows of the A stage are cube channels k = p*4 + dh*2 + dw, columns 64 positions ----
-  __device__ void synth_begin(Unit, uint8_t* ex, int t) const {
-    uint8_t* pi = ex + g.F * (g.K + 4) * 4;
-    uint8_t* pj = pi + ((g.P + 15) & ~15);
-    for (int e = t; e < g.P; e += 256) { pi[e] = (uint8_t)pair_i[e]; pj[e] = (uint8_t)pair_j[e]; }
-    reinterpret_cast<int*>(pj + ((g.P + 15) & ~15))[0] = -1;  // sample whose rows are staged
+  // A thread owns one channel row (pair, dh, dw) for the whole unit.  Its 16 values o_j[2w+dw] only
+  // change with the sample (every 4 stages), so they live in registers; per stage it reads two
+  // o_i[2h+dh] scalars and writes 4 x 16 bytes.
+  struct SynthState { float oj[16]; int sample; int oi_off; int oj_off; };
+  __device__ void synth_begin(Unit un, uint8_t* ex, int t, SynthState& st) const {
+    const int KS = g.K + 4;                               // padded row stride: rows of different fields hit different banks
+    int* staged = reinterpret_cast<int*>(ex + (g.F + 1) * KS * 4);
+    if (t == 0) *staged = -1;                             // sample whose rows are staged
+    for (int e = t; e < KS; e += 256) reinterpret_cast<float*>(ex)[g.F * KS + e] = 0.f;   // zero row for padded pairs
+    st.sample = -1;
+    const int kk = un.m_tile * BM + (t & 127);
+    const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
+    const bool live = pr < g.P;
+    st.oi_off = (live ? pair_i[pr] : g.F) * KS + dh;
+    st.oj_off = (live ? pair_j[pr] : g.F) * KS + dw;
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex_c) const {
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex_c, SynthState& st) const {
     uint8_t* ex = const_cast<uint8_t*>(ex_c);
     const int t = t256 & 127, half = t256 >> 7;
+    const int KS = g.K + 4;
     float* o = reinterpret_cast<float*>(ex);
-    const uint8_t* pi = ex + g.F * (g.K + 4) * 4;
-    const uint8_t* pj = pi + ((g.P + 15) & ~15);
-    int* staged = reinterpret_cast<int*>(const_cast<uint8_t*>(pj) + ((g.P + 15) & ~15));
+    int* staged = reinterpret_cast<int*>(ex + (g.F + 1) * KS * 4);
     const int m0 = (un.z * chunks_per_split + kc) * BK;   // 64 positions: 4 h-rows x 16 w of one sample
     const int b = m0 >> 8, hb = (m0 >> 4) & 15;
-    const int KS = g.K + 4;                               // padded row stride: rows of different fields hit different banks
     if (*staged != b) {                                   // uniform across the 256 producer threads
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int K4 = g.K / 4;
@@ -472,22 +480,19 @@ struct ConvWgradTC : KMajorA, MNMajorB {
       if (t256 == 0) *staged = b;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const int kk = un.m_tile * BM + t;
-    const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
-    const bool live = pr < g.P;
-    const float* oi = o + (live ? pi[pr] : 0) * KS + dh;
-    const float4* oj4 = reinterpret_cast<const float4*>(o + (live ? pj[pr] : 0) * KS);
+    if (st.sample != b) {
+      st.sample = b;
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {                      // chunk c: 8 positions, h = hb + c/2, w = (c&1)*8 .. +7
-      const int c = half * 4 + c4;
-      const float a = live ? oi[2 * (hb + (c >> 1))] : 0.f;
+      for (int wv = 0; wv < 16; ++wv) st.oj[wv] = o[st.oj_off + 2 * wv];
+    }
+    const float* oi = o + st.oi_off + 2 * (hb + half * 2);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {                      // chunk c = half*4 + c4: h = hb + c/2, w = (c&1)*8 .. +7
+      const float a = oi[2 * (c4 >> 1)];
       uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {                       // o_j[2w+dw] for two positions per 16-byte load
-        const float4 q = oj4[(c & 1) * 4 + e];
-        pk[e] = dw ? pack2(a * q.y, a * q.w) : pack2(a * q.x, a * q.z);
-      }
-      *reinterpret_cast<uint4*>(sA + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * st.oj[(c4 & 1) * 8 + 2 * e], a * st.oj[(c4 & 1) * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(sA + sw128_offset(t, half * 4 + c4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   struct Epilogue {

@@ -51,8 +51,9 @@ struct PlainGemm : KMajorA, KMajorB {
   __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * BN); }
-  __device__ void synth_begin(Unit, uint8_t*, int) const {}
-  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct SynthState {};
+  __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
     const PlainGemm& p; int row;
     __device__ Epilogue(const PlainGemm& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}
@@ -90,8 +91,9 @@ struct PlainGemmTN : MNMajorA, MNMajorB {
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
     for (int i = 0; i < BN / 64; ++i) tma_load_2d(s + i * 8192, &mapB, bar, un.n_tile * BN + i * 64, kc * BK);
   }
-  __device__ void synth_begin(Unit, uint8_t*, int) const {}
-  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*) const {}
+  struct SynthState {};
+  __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
+  __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
     const PlainGemmTN& p; int row;
     __device__ Epilogue(const PlainGemmTN& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}

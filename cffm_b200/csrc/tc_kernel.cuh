@@ -65,8 +65,8 @@ struct MNMajorB {
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
 //   void load_b(uint8_t* sB, uint64_t* bar, Unit, int kc) const      -- TMA for the B stage
 //   uint32_t tx_bytes() const                                        -- bytes the TMA loads deliver per stage
-//   void synth_begin(Unit, uint8_t* extra, int t) const              -- kSynthA: per-unit staging (256 threads)
-//   void synth_a(uint8_t* sA, Unit, int kc, int row, const uint8_t* extra) const
+//   struct SynthState; void synth_begin(Unit, uint8_t* extra, int t, SynthState&) const  -- kSynthA: per-unit staging
+//   void synth_a(uint8_t* sA, Unit, int kc, int t, const uint8_t* extra, SynthState&) const  (256 threads)
 //   uint64_t a_desc(addr, k), b_desc(addr, k); uint32_t idesc()      -- UMMA descriptors (see KMajorA ...)
 //   epilogue object: see each policy
 template <class P>
@@ -170,16 +170,17 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
     // ------------------------------------------------------------------ A synthesis (kSynthA only)
     if constexpr (P::kSynthA) {
       const int t = (warp - 6) * 32 + lane;  // 256 producer threads: row t & 127, half (t >> 7) of the stage row
+      typename P::SynthState sst;            // per-thread producer state that lives across stages
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
         const int KC = prm.k_chunks(un);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        prm.synth_begin(un, extra_synth, t);
+        prm.synth_begin(un, extra_synth, t, sst);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra_synth);
+          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra_synth, sst);
           fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->full[stage]);
