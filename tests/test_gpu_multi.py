@@ -1,0 +1,33 @@
+"""Data parallelism over NCCL: N ranks x B/N samples == 1 rank x B samples (needs >= 2 GPUs)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.timeout(280)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_data_parallel_equals_single_gpu(tmp_path, precision):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    out = tmp_path / "dp.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(HERE, "dp_worker.py"), str(out), precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=260)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["replicas_identical"]
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    for a, b in zip(res["losses"], res["ref_losses"]):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (res["losses"], res["ref_losses"])
+    # Adagrad with acc0 = 1e-8: a gradient that is ~0 may flip a +-lr step between summation orders
+    lim = 0.02 if precision == "fp32" else 0.2
+    bad = {k: v for k, v in res["frac_over_2e-3"].items() if v > lim}
+    assert not bad, bad
