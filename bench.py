@@ -292,6 +292,8 @@ def run_ours(args):
         }
         print(json.dumps(line))
         sys.stdout.flush()
+    # tear down together: ncclCommDestroy must not race with a rank that is still working
+    barrier()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -66,8 +66,14 @@ extern "C" int cffm_create(const cffm_config* cfg, cffm_handle** out) {
 
 extern "C" int cffm_destroy(cffm_handle* h) {
   if (!h) return CFFM_OK;
-  comm_destroy(&h->m);
-  model_free(&h->m);
+  Model* m = &h->m;
+  if (m->device >= 0) cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaDeviceSynchronize();
+  // a captured step holds NCCL kernels: the graph has to go before the communicator
+  if (m->step_graph) { cudaGraphExecDestroy(m->step_graph); m->step_graph = nullptr; }
+  comm_destroy(m);
+  model_free(m);
   delete h;
   return CFFM_OK;
 }

@@ -50,8 +50,8 @@ def main():
         with open(out_path, "w") as f:
             json.dump(res, f)
         ref.close()
-    eng.close()
     dist.barrier()
+    eng.close()
     dist.destroy_process_group()
 
 
