@@ -52,7 +52,7 @@ __device__ __forceinline__ float phi_scale() { return ACT == CFFM_ACT_SELU ? kSe
 template <int ACT, bool L0>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
-  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2;
   CUtensorMap mapA, mapB;
   Geom g;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
@@ -158,7 +158,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
 template <int ACT>
 struct ConvDgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
-  static constexpr int kStages = 4, kExtraBytes = 0;
+  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2;
   CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
@@ -222,7 +222,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 // =================================================================================================
 struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
-  static constexpr int kStages = 3, kExtraBytes = 64 * 1024;
+  static constexpr int kStages = 3, kExtraBytes = 64 * 1024, kATiles = 1, kAccBufs = 2;
   CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // Ho = 16: 256 rows per sample
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
@@ -402,7 +402,11 @@ struct Conv0DgradTC : KMajorA, KMajorB {
 template <int ACT, bool L0>
 struct ConvWgradTC : KMajorA, MNMajorB {
   static constexpr bool kSynthA = L0;
-  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0;
+  // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
+  // their accumulators sit side by side in TMEM (2 x 256 columns, one buffer: the units are long)
+  static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2;
+  static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
+  static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
   CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
   Geom g;                   // BN divides Pp, multiple of 64
   int chunks_total, chunks_per_split, n_split;
@@ -414,7 +418,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   }
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN, !L0, true); }
   __device__ int bn() const { return g.BN; }
-  __device__ int m_tiles() const { return 4 * g.Pp / BM; }
+  __device__ int m_tiles() const { return 4 * g.Pp / kRows; }
   __device__ int n_units() const { return m_tiles() * g.tiles_n * n_split; }
   __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
   __device__ Unit unit(int cta, int ncta, int it) const {
@@ -435,7 +439,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int kk0 = (un.m_tile * 2 + i) * 64;
+      const int kk0 = (un.m_tile * (kRows / 64) + i) * 64;
       const int dh = kk0 / (2 * g.Pp), c0 = kk0 - dh * 2 * g.Pp;
       tma_load_5d(s + i * 8192, &mapA, bar, c0, 0, dh, h0, b0);
     }
@@ -455,7 +459,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     if (t == 0) *staged = -1;                             // sample whose rows are staged
     for (int e = t; e < KS; e += 256) reinterpret_cast<float*>(ex)[g.F * KS + e] = 0.f;   // zero row for padded pairs
     st.sample = -1;
-    const int kk = un.m_tile * BM + (t & 127);
+    const int kk = un.m_tile * kRows + t;               // this thread's channel row of the 256-row stage
     const int pr = kk >> 2, dh = (kk >> 1) & 1, dw = kk & 1;
     const bool live = pr < g.P;
     st.oi_off = (live ? pair_i[pr] : g.F) * KS + dh;
@@ -463,7 +467,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   }
   __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex_c, SynthState& st) const {
     uint8_t* ex = const_cast<uint8_t*>(ex_c);
-    const int t = t256 & 127, half = t256 >> 7;
+    const int t = t256 & 127, tile = t256 >> 7;          // row inside its 128-row tile; which of the two A tiles
     const int KS = g.K + 4;
     float* o = reinterpret_cast<float*>(ex);
     int* staged = reinterpret_cast<int*>(ex + (g.F + 1) * KS * 4);
@@ -485,14 +489,15 @@ struct ConvWgradTC : KMajorA, MNMajorB {
 #pragma unroll
       for (int wv = 0; wv < 16; ++wv) st.oj[wv] = o[st.oj_off + 2 * wv];
     }
-    const float* oi = o + st.oi_off + 2 * (hb + half * 2);
+    const float* oi = o + st.oi_off + 2 * hb;
+    uint8_t* sT = sA + tile * A_STAGE_BYTES;
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {                      // chunk c = half*4 + c4: h = hb + c/2, w = (c&1)*8 .. +7
-      const float a = oi[2 * (c4 >> 1)];
+    for (int c = 0; c < 8; ++c) {                         // chunk c: 8 positions, h = hb + c/2, w = (c&1)*8 .. +7
+      const float a = oi[2 * (c >> 1)];
       uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * st.oj[(c4 & 1) * 8 + 2 * e], a * st.oj[(c4 & 1) * 8 + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(sA + sw128_offset(t, half * 4 + c4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * st.oj[(c & 1) * 8 + 2 * e], a * st.oj[(c & 1) * 8 + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(sT + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   struct Epilogue {
@@ -500,8 +505,9 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     __device__ Epilogue(const ConvWgradTC& p_, uint8_t*, int row_, int) : p(p_), row(row_) {}
     __device__ void begin(Unit) {}
     __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
-      float4* dst = reinterpret_cast<float4*>(p.partial + ((int64_t)un.z * 4 * p.g.Pp + un.m_tile * BM + row) * p.g.Pp +
-                                              un.n_tile * p.g.BN + c0);
+      const int at = c0 / p.g.BN, cc = c0 - at * p.g.BN;   // accumulator of A tile `at`
+      float4* dst = reinterpret_cast<float4*>(p.partial + ((int64_t)un.z * 4 * p.g.Pp + un.m_tile * kRows + at * BM + row) * p.g.Pp +
+                                              un.n_tile * p.g.BN + cc);
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) dst[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
     }
@@ -785,12 +791,18 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
     {  // weight gradient
       const std::string tag = "conv_wgrad_l" + std::to_string(l);
       CFFM_PROF(m, tag.c_str(), s);
-      const int tiles = (4 * Pp / BM) * gm.tiles_n;
+      const int rows_per_unit = l == 0 ? 2 * BM : BM;
+      const int tiles = (4 * Pp / rows_per_unit) * gm.tiles_n;
       const int chunks_total = (int)((rows + BK - 1) / BK);
-      int want = (2 * 148 + tiles - 1) / tiles;
-      if ((int64_t)want * 4 * Pp * Pp > st->wg_partial_floats) want = (int)(st->wg_partial_floats / (4ll * Pp * Pp));
-      if (want > chunks_total) want = chunks_total;
-      if (want < 1) want = 1;
+      // split factor: fill whole waves of 148 persistent CTAs (units = tiles * split)
+      int want = 1; double best = 0.0;
+      const int max_split = (int)std::min<int64_t>(st->wg_partial_floats / (4ll * Pp * Pp), chunks_total);
+      for (int sfac = 1; sfac <= max_split && sfac * tiles <= 4 * 148; ++sfac) {
+        const int units = sfac * tiles;
+        const double eff = (double)units / (148.0 * ((units + 147) / 148));
+        const double score = eff * (units >= 148 ? 1.0 : (double)units / 148.0);
+        if (score > best + 1e-9) { best = score; want = sfac; }
+      }
       const int cps = (chunks_total + want - 1) / want;
       const int n_split = (chunks_total + cps - 1) / cps;
       if (l == 0) {

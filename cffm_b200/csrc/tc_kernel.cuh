@@ -32,12 +32,12 @@ constexpr int CTL_BYTES = (sizeof(Ctl) + 63) & ~63;
 // dynamic shared memory of a policy: 1 KB alignment slack + stages + control block + policy scratch
 template <class P>
 constexpr size_t smem_bytes() {
-  return 1024 + (size_t)P::kStages * (A_STAGE_BYTES + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
+  return 1024 + (size_t)P::kStages * (P::kATiles * A_STAGE_BYTES + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
 }
 
-__device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
+__device__ __forceinline__ uint32_t tmem_cols_for(int cols) {
   uint32_t c = 32;
-  while ((int)c < 2 * bn) c <<= 1;
+  while ((int)c < cols) c <<= 1;
   return c;
 }
 
@@ -60,6 +60,8 @@ struct MNMajorB {
 // Policy interface (all __device__):
 //   static constexpr bool kSynthA
 //   static constexpr int kStages, kExtraBytes (policy scratch; the second half belongs to the synth warps)
+//   static constexpr int kATiles (128-row A tiles that share one B stage: accumulators side by side in TMEM),
+//                        kAccBufs (1 or 2 accumulator buffers; kAccBufs * kATiles * bn() <= 512 columns)
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
 //   int k_chunks(Unit) const (>= 1); int bn() const  (UMMA N of this launch)
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   constexpr int STAGES = P::kStages;
-  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
+  constexpr int A_BYTES = P::kATiles * A_STAGE_BYTES;
+  uint8_t* sB = sA + STAGES * A_BYTES;
   Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_STAGE_BYTES_MAX);
   uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + CTL_BYTES;
   uint8_t* extra_synth = extra + P::kExtraBytes / 2;
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int BN = prm.bn();
-  const uint32_t ncols = tmem_cols_for(BN);
+  const int ACC_COLS = P::kATiles * BN;      // TMEM columns of one accumulator buffer
+  const uint32_t ncols = tmem_cols_for(P::kAccBufs * ACC_COLS);
   const int n_iters = prm.n_iters((int)blockIdx.x, (int)gridDim.x);
 
   if (warp == 0 && lane == 0) prm.prefetch();
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
-          if constexpr (!P::kSynthA) prm.load_a(sA + stage * A_STAGE_BYTES, &ctl->full[stage], un, kc);
+          if constexpr (!P::kSynthA) prm.load_a(sA + stage * A_BYTES, &ctl->full[stage], un, kc);
           prm.load_b(sB + stage * B_STAGE_BYTES_MAX, &ctl->full[stage], un, kc);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -125,20 +129,23 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
         const int KC = prm.k_chunks(prm.unit((int)blockIdx.x, (int)gridDim.x, it));
         mbar_wait(&ctl->tempty[buf], bphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES_MAX);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d_tmem, prm.a_desc(a_addr, k), prm.b_desc(b_addr, k), idesc, (kc | k) != 0);
+          for (int at = 0; at < P::kATiles; ++at)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem + (uint32_t)(at * BN), prm.a_desc(a_addr + at * A_STAGE_BYTES, k), prm.b_desc(b_addr, k), idesc,
+                        (kc | k) != 0);
           umma_commit(&ctl->empty[stage]);              // frees the smem stage when these MMAs retire
           if (kc == KC - 1) umma_commit(&ctl->tfull[buf]);  // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        buf ^= 1; if (buf == 0) bphase ^= 1;
+        if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
       }
     }
   } else if (warp < 6) {
@@ -151,9 +158,9 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
       mbar_wait(&ctl->tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
       epi.begin(un);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < ACC_COLS; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->tempty[buf]);   // accumulator buffer may be overwritten
       epi.end(un);
-      buf ^= 1; if (buf == 0) bphase ^= 1;
+      if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
     }
     epi.finish();
   } else {
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          prm.synth_a(sA + stage * A_STAGE_BYTES, un, kc, t, extra_synth, sst);
+          prm.synth_a(sA + stage * A_BYTES, un, kc, t, extra_synth, sst);
           fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->full[stage]);
