@@ -52,7 +52,7 @@ __device__ __forceinline__ float phi_scale() { return ACT == CFFM_ACT_SELU ? kSe
 template <int ACT, bool L0>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
-  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
   CUtensorMap mapA, mapB;
   Geom g;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
@@ -158,7 +158,9 @@ struct ConvFwdTC : KMajorA, KMajorB {
 template <int ACT>
 struct ConvDgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
-  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2;
+  // the reduction is short (Pp/64 stages per tile) and the epilogue waits on global loads of the mask:
+  // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks) keep up with the MMA
+  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
   CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
@@ -222,7 +224,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 // =================================================================================================
 struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
-  static constexpr int kStages = 3, kExtraBytes = 64 * 1024, kATiles = 1, kAccBufs = 2;
+  static constexpr int kStages = 3, kExtraBytes = 72 * 1024, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
   CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // Ho = 16: 256 rows per sample
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
@@ -245,27 +247,27 @@ struct Conv0DgradTC : KMajorA, KMajorB {
   __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
     const Conv0DgradTC& p; int row, ew, lane;
-    float *o, *dOi, *dOj;   // smem: rows [F*K], d o_i [F*K], per-warp d o_j slices [4][F*K]
+    float *o, *dOi, *dOj;   // smem: rows [F*K], d o_i [2][F*K] (one per warp of a lane quarter), per-warp d o_j slices [8][F*K]
     uint8_t *pi, *pj;
     float dsp0, dsp1; int h, w;
     __device__ Epilogue(const Conv0DgradTC& p_, uint8_t* ex, int row_, int ew_) : p(p_), row(row_), ew(ew_) {
       const int FK = p.g.F * p.g.K;
       lane = threadIdx.x & 31;
-      o = reinterpret_cast<float*>(ex); dOi = o + FK; dOj = dOi + FK;
-      pi = reinterpret_cast<uint8_t*>(dOj + 4 * FK); pj = pi + ((p.g.P + 15) & ~15);
+      o = reinterpret_cast<float*>(ex); dOi = o + FK; dOj = dOi + 2 * FK;
+      pi = reinterpret_cast<uint8_t*>(dOj + 8 * FK); pj = pi + ((p.g.P + 15) & ~15);
       const int t = ew * 32 + lane;
-      for (int e = t; e < p.g.P; e += 128) { pi[e] = (uint8_t)p.pair_i[e]; pj[e] = (uint8_t)p.pair_j[e]; }
+      for (int e = t; e < p.g.P; e += 256) { pi[e] = (uint8_t)p.pair_i[e]; pj[e] = (uint8_t)p.pair_j[e]; }
       dsp0 = dsp1 = 0.f; h = w = 0;
     }
-    __device__ void epi_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+    __device__ void epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
     __device__ void begin(Unit un) {
       const int FK = p.g.F * p.g.K, t = ew * 32 + lane;
       const int b = un.m_tile >> 1;
       if (un.z == 0) {  // first unit of a sample: stage its rows, clear the accumulators
         epi_sync();
         const float* src = p.rows + (int64_t)b * FK;
-        for (int e = t; e < FK; e += 128) { o[e] = __ldg(src + e); dOi[e] = 0.f; }
-        for (int e = t; e < 4 * FK; e += 128) dOj[e] = 0.f;
+        for (int e = t; e < FK; e += 256) o[e] = __ldg(src + e);
+        for (int e = t; e < 10 * FK; e += 256) dOi[e] = 0.f;   // both d o_i copies and the eight d o_j slices
         epi_sync();
       }
       const int r = (un.m_tile & 1) * BM + row;   // position inside the sample
@@ -311,7 +313,7 @@ struct Conv0DgradTC : KMajorA, KMajorB {
         float x = (b2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, b2 ? x0 : x1, 4);
         x += __shfl_xor_sync(0xffffffffu, x, 2);
         x += __shfl_xor_sync(0xffffffffu, x, 1);
-        if ((lane & 3) == 0 && (!b3 || n1)) atomicAdd(dOi + (b3 ? i1 : i0) * K + 2 * h + (b2 ? 1 : 0), x);
+        if ((lane & 3) == 0 && (!b3 || n1)) atomicAdd(dOi + (ew >> 2) * F * K + (b3 ? i1 : i0) * K + 2 * h + (b2 ? 1 : 0), x);
       }
       // d o_j: the warp's two h rows are lanes l and l^16; the lower half keeps dw = 0, the upper dw = 1
 #pragma unroll
@@ -354,7 +356,7 @@ struct Conv0DgradTC : KMajorA, KMajorB {
         const int r = lane & 15, pr = pbase + (r >> 1);
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
-          if ((r >> 1) == pp && pr < p.g.P) dOi[pi[pr] * K + 2 * h + (r & 1)] += ci[0];
+          if ((r >> 1) == pp && pr < p.g.P) dOi[(ew >> 2) * p.g.F * K + pi[pr] * K + 2 * h + (r & 1)] += ci[0];
           __syncwarp();
         }
       }
@@ -387,7 +389,12 @@ struct Conv0DgradTC : KMajorA, KMajorB {
       const int b = un.m_tile >> 1;
       epi_sync();
       float* dst = p.g_rows + (int64_t)b * FK;
-      for (int e = t; e < FK; e += 128) dst[e] = dOi[e] + ((dOj[e] + dOj[FK + e]) + (dOj[2 * FK + e] + dOj[3 * FK + e]));
+      for (int e = t; e < FK; e += 256) {
+        float sj = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) sj += dOj[sl * FK + e];
+        dst[e] = (dOi[e] + dOi[FK + e]) + sj;
+      }
     }
     __device__ void finish() {}
   };
@@ -404,7 +411,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   static constexpr bool kSynthA = L0;
   // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
   // their accumulators sit side by side in TMEM (2 x 256 columns, one buffer: the units are long)
-  static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2;
+  static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2, kEpiWarps = 4;
   static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
   static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
   CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
@@ -629,7 +636,7 @@ int tc_supported(Model* m) {
   if (!m->cfg.outer_conv) return CFFM_OK;
   if (m->Ko != 32) { m->err = "precision bf16 needs outer_dims == 32 (other sizes run in fp32)"; return CFFM_ERR_UNSUPPORTED; }
   if (m->cfg.activation == CFFM_ACT_GELU) { m->err = "precision bf16 does not support gelu yet (its derivative needs the pre-activation)"; return CFFM_ERR_UNSUPPORTED; }
-  if (m->F > 48) { m->err = "precision bf16 needs num_field <= 48"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->F > 48) { m->err = "precision bf16 needs num_field <= 48"; return CFFM_ERR_UNSUPPORTED; }  // dgrad0 smem: 11*F*K*4 B
   return CFFM_OK;
 }
 
@@ -705,7 +712,7 @@ static int launch_tc(Model* m, const Pol& p, int units_hint, cudaStream_t s) {
   }
   int grid = units_hint < 148 ? units_hint : 148;
   if (grid < 1) grid = 1;
-  k_tc<Pol><<<grid, Pol::kSynthA ? SYNTH_THREADS : BASE_THREADS, smem_bytes<Pol>(), s>>>(p);
+  k_tc<Pol><<<grid, block_threads<Pol>(), smem_bytes<Pol>(), s>>>(p);
   m->launches++;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;

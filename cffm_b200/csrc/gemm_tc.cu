@@ -39,7 +39,7 @@ namespace tc {
 struct PlainGemm : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN); }
-  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2;
+  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
   CUtensorMap mapA, mapB;   // A: dims (K, M) box (64, 128); B: dims (K, N) box (64, BN)
   float* C; int M, N, K, BN, tiles_n;
   __device__ int bn() const { return BN; }
@@ -74,7 +74,7 @@ struct PlainGemm : KMajorA, KMajorB {
 // ---- TN GEMM policy: C[M,N] = sum_r A[r,M] B[r,N] (both operands MN-major) ---------------------
 struct PlainGemmTN : MNMajorA, MNMajorB {
   static constexpr bool kSynthA = false;
-  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2;
+  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
   CUtensorMap mapA, mapB;   // A: dims (M, R) box (64, 64); B: dims (N, R) box (64, 64)
   float* C; int M, N, R, BN, tiles_n;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN, true, true); }
@@ -143,7 +143,7 @@ int tc_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K, cu
   const int units = ((M + BM - 1) / BM) * p.tiles_n;
   int grid = units < 148 ? units : 148;
   if (grid < 1) grid = 1;
-  k_tc<PlainGemm><<<grid, BASE_THREADS, smem_bytes<PlainGemm>(), s>>>(p);
+  k_tc<PlainGemm><<<grid, block_threads<PlainGemm>(), smem_bytes<PlainGemm>(), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
   return CFFM_OK;
@@ -173,7 +173,7 @@ int tc_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int R,
   }
   const int units = ((M + BM - 1) / BM) * p.tiles_n;
   int grid = units < 148 ? units : 148;
-  k_tc<PlainGemmTN><<<grid, BASE_THREADS, smem_bytes<PlainGemmTN>(), s>>>(p);
+  k_tc<PlainGemmTN><<<grid, block_threads<PlainGemmTN>(), smem_bytes<PlainGemmTN>(), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
   return CFFM_OK;

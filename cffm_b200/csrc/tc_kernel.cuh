@@ -2,9 +2,9 @@
 //
 //   warp 0        : TMA producer (one elected lane): operand tiles -> shared memory stages
 //   warp 1        : MMA issuer (lane 0): tcgen05.mma over the stages, accumulators in TMEM
-//   warps 2..5    : epilogue: tcgen05.ld TMEM -> registers -> policy epilogue (bias, activation,
+//   warps 2..5(9) : epilogue: tcgen05.ld TMEM -> registers -> policy epilogue (bias, activation,
 //                   pooling sums, gradient contractions ...) -> global memory
-//   warps 6..13   : (policies with kSynthA) build the A stage in shared memory themselves, in the
+//   next 8 warps  : (policies with kSynthA) build the A stage in shared memory themselves, in the
 //                   UMMA SWIZZLE_128B layout -- used for the interaction cube, which never exists
 //                   in HBM (CFFM.py:355-367)
 //
@@ -19,7 +19,9 @@ namespace tc {
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int B_STAGE_BYTES_MAX = MAX_BN * BK * 2;
-constexpr int BASE_THREADS = 192, SYNTH_WARPS = 8, SYNTH_THREADS = BASE_THREADS + 32 * SYNTH_WARPS;
+constexpr int SYNTH_WARPS = 8;
+template <class P>
+constexpr int block_threads() { return 64 + 32 * P::kEpiWarps + (P::kSynthA ? 32 * SYNTH_WARPS : 0); }
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct Ctl {
@@ -60,6 +62,7 @@ struct MNMajorB {
 // Policy interface (all __device__):
 //   static constexpr bool kSynthA
 //   static constexpr int kStages, kExtraBytes (policy scratch; the second half belongs to the synth warps)
+//   static constexpr int kEpiWarps (4, or 8: two warps per TMEM lane quarter taking alternate 32-column chunks),
 //   static constexpr int kATiles (128-row A tiles that share one B stage: accumulators side by side in TMEM),
 //                        kAccBufs (1 or 2 accumulator buffers; kAccBufs * kATiles * bn() <= 512 columns)
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
@@ -72,7 +75,7 @@ struct MNMajorB {
 //   uint64_t a_desc(addr, k), b_desc(addr, k); uint32_t idesc()      -- UMMA descriptors (see KMajorA ...)
 //   epilogue object: see each policy
 template <class P>
-__global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) k_tc(const __grid_constant__ P prm) {
+__global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_constant__ P prm) {
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array (an integer round trip would make
   // every access below a generic LD/ST instead of LDS/STS)
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   if (warp == 0 && lane == 0) prm.prefetch();
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? SYNTH_WARPS : 0)); mbar_init(&ctl->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], P::kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&ctl->tmem_base, ncols);
@@ -148,10 +151,11 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
         if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + P::kEpiWarps) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // row inside the 128-row tile
+    const int sub = (warp - 2) >> 2;        // kEpiWarps == 8: which of the two warps of this quarter
     typename P::Epilogue epi(prm, extra, row, warp - 2);
     int buf = 0; uint32_t bphase = 0;
     for (int it = 0; it < n_iters; ++it) {
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
       const uint32_t taddr = tmem_base + (uint32_t)(buf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
       epi.begin(un);
       for (int c0 = 0; c0 < ACC_COLS; c0 += 32) {
+        if (P::kEpiWarps == 8 && ((c0 >> 5) & 1) != sub) continue;
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(P::kSynthA ? SYNTH_THREADS : BASE_THREADS, 1) 
   } else {
     // ------------------------------------------------------------------ A synthesis (kSynthA only)
     if constexpr (P::kSynthA) {
-      const int t = (warp - 6) * 32 + lane;  // 256 producer threads: row t & 127, half (t >> 7) of the stage row
+      const int t = (warp - 2 - P::kEpiWarps) * 32 + lane;  // 256 producer threads
       typename P::SynthState sst;            // per-thread producer state that lives across stages
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
