@@ -116,6 +116,11 @@ def _declare(lib):
         "cffm_train_submit_host": (C.c_int, [vp, vp, vp, i64, P(f32), P(i32)]),
         "cffm_train_flush": (C.c_int, [vp, P(f32), P(i32)]),
         "cffm_evaluate_host": (C.c_int, [vp, vp, vp, i64, i64, P(C.c_double), P(C.c_double)]),
+        "cffm_dataset_upload": (C.c_int, [vp, vp, vp, i64]),
+        "cffm_dataset_permute": (C.c_int, [vp, vp]),
+        "cffm_train_block": (C.c_int, [vp, i64, i64]),
+        "cffm_last_loss": (C.c_int, [vp, P(f32)]),
+        "cffm_dataset_evaluate": (C.c_int, [vp, i64, P(C.c_double), P(C.c_double)]),
         "cffm_synchronize": (C.c_int, [vp]),
         "cffm_launch_count": (i64, [vp]),
         "cffm_profile_enable": (C.c_int, [vp, i32]),

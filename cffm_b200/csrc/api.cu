@@ -458,6 +458,117 @@ extern "C" int cffm_evaluate_host(cffm_handle* h, const int32_t* ids_host, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Resident training set.
+__global__ void k_permute_rows(const int32_t* __restrict__ ids, const float* __restrict__ y, const int64_t* __restrict__ perm,
+                               int64_t N, int F, int32_t* __restrict__ ids_out, float* __restrict__ y_out) {
+  const int64_t total = N * F;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / F; const int f = (int)(e - r * F);
+    const int64_t src = perm[r];
+    ids_out[e] = ids[src * F + f];
+    if (f == 0) y_out[r] = y[src];
+  }
+}
+
+extern "C" int cffm_dataset_upload(cffm_handle* h, const int32_t* ids_host, const float* labels_host, int64_t N) {
+  API_BEGIN
+  if (!h || !ids_host || !labels_host || N < 1) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  void* old[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
+  for (void* p : old) if (p) cudaFree(p);
+  m->ds_ids = m->ds_ids_tmp = nullptr; m->ds_labels = m->ds_labels_tmp = nullptr; m->ds_perm = nullptr; m->ds_N = 0;
+  const int F = m->F;
+  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_ids, sizeof(int32_t) * N * F));
+  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_ids_tmp, sizeof(int32_t) * N * F));
+  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_labels, sizeof(float) * N));
+  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_labels_tmp, sizeof(float) * N));
+  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_perm, sizeof(int64_t) * N));
+  CFFM_CUDA_OK(m, cudaMemcpy(m->ds_ids, ids_host, sizeof(int32_t) * N * F, cudaMemcpyHostToDevice));
+  CFFM_CUDA_OK(m, cudaMemcpy(m->ds_labels, labels_host, sizeof(float) * N, cudaMemcpyHostToDevice));
+  m->ds_N = N;
+  return CFFM_OK;
+  API_END(h)
+}
+
+extern "C" int cffm_dataset_permute(cffm_handle* h, const int64_t* perm_host) {
+  API_BEGIN
+  if (!h || !perm_host) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  if (!m->ds_N) { m->err = "no resident dataset"; return CFFM_ERR_INVALID; }
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  CFFM_CUDA_OK(m, cudaMemcpyAsync(m->ds_perm, perm_host, sizeof(int64_t) * m->ds_N, cudaMemcpyHostToDevice, m->stream));
+  const int64_t total = m->ds_N * m->F;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  k_permute_rows<<<blocks, 256, 0, m->stream>>>(m->ds_ids, m->ds_labels, m->ds_perm, m->ds_N, m->F, m->ds_ids_tmp, m->ds_labels_tmp);
+  m->launches++;
+  std::swap(m->ds_ids, m->ds_ids_tmp); std::swap(m->ds_labels, m->ds_labels_tmp);
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));  // perm_host may be freed by the caller
+  return CFFM_OK;
+  API_END(h)
+}
+
+extern "C" int cffm_train_block(cffm_handle* h, int64_t start, int64_t B) {
+  API_BEGIN
+  if (!h) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  int r = check_batch(m, B); if (r != CFFM_OK) return r;
+  if (start < 0 || start + B > m->ds_N) { m->err = "block outside the resident dataset"; return CFFM_ERR_INVALID; }
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  r = model_alloc_train(m); if (r != CFFM_OK) return r;
+  CFFM_CUDA_OK(m, cudaMemcpyAsync(m->ids_buf, m->ds_ids + start * m->F, sizeof(int32_t) * B * m->F, cudaMemcpyDeviceToDevice, m->stream));
+  CFFM_CUDA_OK(m, cudaMemcpyAsync(m->labels_buf, m->ds_labels + start, sizeof(float) * B, cudaMemcpyDeviceToDevice, m->stream));
+  r = enqueue_staged_step(m, B, m->stream);
+  m->last_B = B;
+  return r;
+  API_END(h)
+}
+
+extern "C" int cffm_last_loss(cffm_handle* h, float* loss_host) {
+  if (!h || !loss_host) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  CFFM_CUDA_OK(m, cudaMemcpyAsync(m->h_loss[0] + 2, m->loss_out, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  *loss_host = m->h_loss[0][2];
+  return CFFM_OK;
+}
+
+static int evaluate_device(Model* m, const int32_t* ids_dev, const float* y_dev, int64_t N, int64_t batch, double* rmse, double* r2) {
+  k_label_stats<<<1, 1024, 0, m->stream>>>(y_dev, N, m->eval_acc);
+  m->launches++;
+  int rc = CFFM_OK;
+  for (int64_t o = 0; o < N && rc == CFFM_OK; o += batch) {
+    const int64_t B = std::min<int64_t>(batch, N - o);
+    rc = run_forward(m, ids_dev + o * m->F, nullptr, B, m->stream);
+    k_sse_clipped<<<1, 1024, 0, m->stream>>>(m->pred, y_dev + o, B, m->eval_acc);
+    m->launches++;
+    m->last_B = B;
+  }
+  if (rc != CFFM_OK) return rc;
+  double acc[5] = {0, 0, 0, 0, 0};
+  CFFM_CUDA_OK(m, cudaMemcpyAsync(acc, m->eval_acc, sizeof(acc), cudaMemcpyDeviceToHost, m->stream));
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  const double sse = acc[4], n = (double)N;
+  const double sst = acc[3] - acc[2] * acc[2] / n;
+  if (rmse) *rmse = sqrt(sse / n);
+  if (r2) *r2 = sst > 0 ? 1.0 - sse / sst : 0.0;
+  return CFFM_OK;
+}
+
+extern "C" int cffm_dataset_evaluate(cffm_handle* h, int64_t batch, double* rmse, double* r2) {
+  API_BEGIN
+  if (!h) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  if (!m->ds_N) { m->err = "no resident dataset"; return CFFM_ERR_INVALID; }
+  if (batch < 1 || batch > m->max_batch) batch = m->max_batch;
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  return evaluate_device(m, m->ds_ids, m->ds_labels, m->ds_N, batch, rmse, r2);
+  API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------
 extern "C" int cffm_op_gather_dev(const float* table_dev, const int32_t* ids_dev, int64_t n, int32_t K, float* out_dev,
                                   void* stream) {
   if (!table_dev || !ids_dev || !out_dev || n < 0 || K < 4 || (K & 3)) { g_err = "bad argument (K must be a multiple of 4)"; return CFFM_ERR_INVALID; }

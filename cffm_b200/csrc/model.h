@@ -130,6 +130,12 @@ struct Model {
 
   // evaluate scratch
   double* eval_acc = nullptr;  // [8] device doubles
+
+  // resident training set (cffm_dataset_*)
+  int32_t *ds_ids = nullptr, *ds_ids_tmp = nullptr;
+  float *ds_labels = nullptr, *ds_labels_tmp = nullptr;
+  int64_t* ds_perm = nullptr;
+  int64_t ds_N = 0;
 };
 
 // ---- implemented across the .cu files ----

@@ -274,6 +274,8 @@ void model_free(Model* m) {
                  m->eval_acc};
   sparse_work_free(&m->sw);
   tc_free(m);
+  void* ds[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
+  for (void* p : ds) if (p) cudaFree(p);
   for (void* p : dev) if (p) cudaFree(p);
   for (int l = 0; l < kMaxConv; ++l) { if (m->Y[l]) cudaFree(m->Y[l]); if (m->dY[l]) cudaFree(m->dY[l]); }
   for (int s = 0; s < 2; ++s) {

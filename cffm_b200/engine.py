@@ -154,6 +154,29 @@ class Engine:
                                                 C.byref(r2)), "cffm_evaluate_host")
         return float(rmse.value), float(r2.value)
 
+    # ------------------------------------------------------------------ resident training set
+    def dataset_upload(self, ids, labels):
+        a = self._ids(ids)
+        y = np.ascontiguousarray(np.asarray(labels, dtype=np.float32).reshape(-1))
+        self._check(self.lib.cffm_dataset_upload(self.h, _ptr(a), _ptr(y), a.shape[0]), "cffm_dataset_upload")
+
+    def dataset_permute(self, perm):
+        p = np.ascontiguousarray(np.asarray(perm, dtype=np.int64))
+        self._check(self.lib.cffm_dataset_permute(self.h, _ptr(p)), "cffm_dataset_permute")
+
+    def train_block(self, start, B):
+        self._check(self.lib.cffm_train_block(self.h, int(start), int(B)), "cffm_train_block")
+
+    def last_loss(self):
+        v = C.c_float()
+        self._check(self.lib.cffm_last_loss(self.h, C.byref(v)), "cffm_last_loss")
+        return float(v.value)
+
+    def dataset_evaluate(self, batch=0):
+        rmse, r2 = C.c_double(), C.c_double()
+        self._check(self.lib.cffm_dataset_evaluate(self.h, int(batch), C.byref(rmse), C.byref(r2)), "cffm_dataset_evaluate")
+        return float(rmse.value), float(r2.value)
+
     # ------------------------------------------------------------------ compute (device buffers)
     def forward_dev(self, ids_ptr, B, out_ptr, stream=0):
         self._check(self.lib.cffm_forward_dev(self.h, C.c_void_p(ids_ptr), int(B), C.c_void_p(out_ptr),

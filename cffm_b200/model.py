@@ -116,17 +116,36 @@ class CFFM:
             te = self.evaluate(data.Test_data)
             logging.info(("Init_RMSE: train=%.4f,validation=%.4f,test=%.4f | Init_R2: train=%.4f,validation=%.4f,"
                           "test=%.4f [%.1f s] " % (tr[0], va[0], te[0], tr[1], va[1], te[1], time() - t2)))
+        # Equal-length rows (every shipped dataset): the training split lives in HBM, an epoch's shuffle is
+        # a device gather and a step reads its contiguous block in place -- no per-step host->device copy.
+        resident = isinstance(data.Train_data['X'], np.ndarray) and data.Train_data['X'].ndim == 2 \
+            and data.Train_data['X'].shape[1] == self.num_field
+        if resident:
+            eng.dataset_upload(data.Train_data['X'], data.Train_data['Y'])
         for epoch in range(self.epoch):
             t1 = time()
-            data.Train_data['X'], data.Train_data['Y'] = _shuffle_in_unison(
-                data.Train_data['X'], data.Train_data['Y'], self.random_seed)  # CFFM.py:183
-            total_batch = int(len(data.Train_data['Y']) / self.batch_size)  # :185
+            n_train = len(data.Train_data['Y'])
+            if resident:
+                perm = np.random.RandomState(self.random_seed).permutation(n_train)  # CFFM.py:183, :556-558
+                data.Train_data['X'], data.Train_data['Y'] = data.Train_data['X'][perm], np.asarray(data.Train_data['Y'])[perm]
+                eng.dataset_permute(perm)
+            else:
+                data.Train_data['X'], data.Train_data['Y'] = _shuffle_in_unison(
+                    data.Train_data['X'], data.Train_data['Y'], self.random_seed)
+            total_batch = int(n_train / self.batch_size)  # :185
             for _ in range(total_batch):
-                blk = self.get_random_block_from_data(data.Train_data, self.batch_size)
-                eng.train_submit(blk['X'], blk['Y'])  # :200, pipelined: loss values are not consumed by the loop
-            eng.train_flush()
+                if resident:
+                    eng.train_block(self._rng.randint(0, n_train - self.batch_size), self.batch_size)  # :188, :561
+                else:
+                    blk = self.get_random_block_from_data(data.Train_data, self.batch_size)
+                    eng.train_submit(blk['X'], blk['Y'])  # :200, pipelined: loss values are not consumed by the loop
+            if resident:
+                eng.synchronize()
+            else:
+                eng.train_flush()
             t2 = time()
-            train_rmse, train_r2 = self.evaluate(data.Train_data)
+            train_rmse, train_r2 = (eng.dataset_evaluate(int(self.eval_batch or self.batch_size)) if resident
+                                    else self.evaluate(data.Train_data))
             valid_rmse, valid_r2 = self.evaluate(data.Validation_data)
             test_rmse, test_r2 = self.evaluate(data.Test_data)
             self.train_rmse.append(train_rmse); self.valid_rmse.append(valid_rmse); self.test_rmse.append(test_rmse)

@@ -138,6 +138,17 @@ int cffm_train_flush(cffm_handle* h, float* loss_host, int32_t* n_losses);
 int cffm_evaluate_host(cffm_handle* h, const int32_t* ids_host, const float* labels_host, int64_t N,
                        int64_t batch, double* rmse, double* r2);
 
+/* ---- resident training set: the loop of CFFM.py:181-200 without per-step host->device copies.
+ *      The split is uploaded once; an epoch's shuffle (sklearn shuffle, CFFM.py:183) is a device gather
+ *      with the host-made permutation (new[i] = old[perm[i]]); a step trains on the contiguous block
+ *      [start, start+B) of the current order (get_random_block_from_data, CFFM.py:560-581), enqueued
+ *      asynchronously; cffm_dataset_evaluate is evaluate() (CFFM.py:583-615) over the resident split. */
+int cffm_dataset_upload(cffm_handle* h, const int32_t* ids_host, const float* labels_host, int64_t N);
+int cffm_dataset_permute(cffm_handle* h, const int64_t* perm_host);
+int cffm_train_block(cffm_handle* h, int64_t start, int64_t B);
+int cffm_last_loss(cffm_handle* h, float* loss_host);
+int cffm_dataset_evaluate(cffm_handle* h, int64_t batch, double* rmse, double* r2);
+
 int cffm_synchronize(cffm_handle* h);
 /* number of kernels launched by the library on this handle since creation */
 int64_t cffm_launch_count(const cffm_handle* h);

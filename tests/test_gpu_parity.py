@@ -317,3 +317,39 @@ def test_errors_are_reported_not_thrown():
     with pytest.raises(CffmError):
         eng.get_param("no_such_variable")
     eng.close()
+
+
+def test_resident_dataset_equals_host_batches():
+    """cffm_dataset_* (split resident in HBM, device shuffle, in-place blocks) == the host-buffer loop."""
+    from cffm_b200 import Engine
+    M, ids, y = _frappe_batch(1024)
+    a = Engine(M, 10, 32, 32, activation="selu", max_batch=128, seed=6)
+    b = Engine(M, 10, 32, 32, activation="selu", max_batch=128, seed=6)
+    perm = np.random.RandomState(2021).permutation(1024)
+    b.dataset_upload(ids, y)
+    b.dataset_permute(perm)
+    ids_p, y_p = ids[perm], y[perm]
+    starts = [5, 700, 896, 333]
+    for st in starts:
+        la = a.train_step(ids_p[st:st + 128], y_p[st:st + 128])
+        b.train_block(st, 128)
+        assert b.last_loss() == la
+    wa, wb = a.get_weights(), b.get_weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+    ra, rb = a.evaluate(ids_p, y_p, 128), b.dataset_evaluate(128)
+    assert ra == rb
+    a.close(); b.close()
+
+
+def test_cli_train_loop_runs_on_the_fixture(tmp_path, monkeypatch):
+    """The reference command line (README) end to end on the Frappe fixture: a few epochs, RMSE improves."""
+    import os
+    from cffm_b200 import cli
+    monkeypatch.chdir(tmp_path)
+    model = cli.main(["--path", os.path.join(GOLDEN, "frappe_mini") + "/", "--dataset", "frappe", "--epoch", "12",
+                      "--batch_size", "256", "--inner_dims", "32", "--outer_dims", "32", "--lamda", "0", "--lr", "0.05",
+                      "--loss_type", "square_loss", "--num_field", "10", "--linear_att", "1", "--inner_conv", "1",
+                      "--outer_conv", "1", "--activation", "selu", "--verbose", "4"])
+    assert len(model.valid_rmse) >= 6 and min(model.valid_rmse) < model.valid_rmse[0]
+    assert min(model.valid_rmse) < 1.0
+    assert os.path.exists(tmp_path / "logging.log")
