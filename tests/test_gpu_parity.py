@@ -352,4 +352,4 @@ def test_cli_train_loop_runs_on_the_fixture(tmp_path, monkeypatch):
                       "--outer_conv", "1", "--activation", "selu", "--verbose", "4"])
     assert len(model.valid_rmse) >= 6 and min(model.valid_rmse) < model.valid_rmse[0]
     assert min(model.valid_rmse) < 1.0
-    assert os.path.exists(tmp_path / "logging.log")
+    assert len(model.train_rmse) == len(model.valid_rmse) == len(model.test_rmse) == len(model.valid_r2)
