@@ -149,24 +149,32 @@ extern "C" int cffm_param_info(const cffm_handle* h, int index, char* name, int 
   return CFFM_OK;
 }
 
-static float* param_ptr(Model* m, const ParamInfo* p, bool accum) {
+// slot 0: the variable; 1: first optimizer slot; 2: second slot (Adam v)
+static float* param_ptr(Model* m, const ParamInfo* p, int slot) {
   switch (p->kind) {
-    case PK_TABLE_INNER: return accum ? m->inner_acc : m->inner_tab;
-    case PK_TABLE_OUTER: return accum ? m->outer_acc : m->outer_tab;
-    case PK_TABLE_BIAS: return accum ? m->fbias_acc : m->fbias_tab;
-    default: return (accum ? m->dense_acc : m->dense_w) + p->offset;
+    case PK_TABLE_INNER: return slot == 0 ? m->inner_tab : (slot == 1 ? m->inner_acc : m->inner_acc2);
+    case PK_TABLE_OUTER: return slot == 0 ? m->outer_tab : (slot == 1 ? m->outer_acc : m->outer_acc2);
+    case PK_TABLE_BIAS: return slot == 0 ? m->fbias_tab : (slot == 1 ? m->fbias_acc : m->fbias_acc2);
+    default: {
+      float* base = slot == 0 ? m->dense_w : (slot == 1 ? m->dense_acc : m->dense_acc2);
+      return base ? base + p->offset : nullptr;
+    }
   }
 }
 
 static int param_copy(cffm_handle* h, const char* name, float* host, int64_t numel, bool accum, bool to_host) {
   if (!h || !name || !host) return CFFM_ERR_INVALID;
   Model* m = &h->m;
-  const ParamInfo* p = model_find(m, name);
+  std::string nm(name);
+  int slot = accum ? 1 : 0;
+  if (accum && nm.size() > 2 && nm.compare(nm.size() - 2, 2, ":2") == 0) { slot = 2; nm.resize(nm.size() - 2); }  // "<name>:2" = Adam v
+  const ParamInfo* p = model_find(m, nm.c_str());
   if (!p) { m->err = std::string("unknown variable: ") + name; return CFFM_ERR_INVALID; }
   if (numel != p->numel) { m->err = std::string("size mismatch for ") + name; return CFFM_ERR_INVALID; }
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
-  float* d = param_ptr(m, p, accum);
+  float* d = param_ptr(m, p, slot);
+  if (!d) { m->err = std::string("this optimizer has no such slot: ") + name; return CFFM_ERR_INVALID; }
   if (to_host) CFFM_CUDA_OK(m, cudaMemcpy(host, d, sizeof(float) * numel, cudaMemcpyDeviceToHost));
   else CFFM_CUDA_OK(m, cudaMemcpy(d, host, sizeof(float) * numel, cudaMemcpyHostToDevice));
   return CFFM_OK;
@@ -599,7 +607,7 @@ extern "C" int cffm_op_sparse_adagrad_dev(float* table_dev, float* accum_dev, in
   if (r == CFFM_OK) {
     SparseTables t;
     t.tab[0] = table_dev; t.acc[0] = accum_dev; t.grads[0] = grads_dev; t.K[0] = K;
-    launch_sparse_adagrad(&w, t, n, lr, s, nullptr);
+    launch_sparse_update(&w, t, n, CFFM_OPT_ADAGRAD, lr, nullptr, s, nullptr);
     if (uniq_dev) k_copy_uniq<<<64, 256, 0, s>>>(w.keys_out, w.seg_start, w.n_uniq, uniq_dev, n_uniq_dev);
   }
   cudaError_t e = cudaStreamSynchronize(s);

@@ -542,6 +542,12 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   const int act = m->cfg.activation;
 
   // ---- loss: (global) sum -> loss value, scale of dLoss/dout ----
+  if (m->cfg.lamda > 0.f && m->cfg.loss_type == CFFM_LOSS_SQUARE) {  // regulariser terms of CFFM.py:489-491
+    CFFM_PROF(m, "l2_reg_sums", s);
+    if (m->cfg.inner_conv) launch_sumsq(m->inner_tab, (int64_t)m->M * m->Ki, m->sumsq_partial, m->scalars + 6, s);
+    if (m->cfg.outer_conv) launch_sumsq(m->outer_tab, (int64_t)m->M * m->Ko, m->sumsq_partial, m->scalars + 7, s);
+    m->launches += 4;
+  }
   launch_loss_sum(m, B, s);
   if (m->world > 1) { int r = comm_allreduce_f32(m, m->scalars, 1, s); if (r != CFFM_OK) return r; }
   launch_loss_finish(m, B, s);
@@ -674,17 +680,29 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     int r;
     { CFFM_PROF(m, "sort_segments", s); r = sparse_sort_segments(&m->sw, upd_ids, n_upd, m->M, s, &m->launches); }
     if (r != CFFM_OK) { m->err = "sparse_sort_segments failed"; return r; }
+    const int opt = m->cfg.optimizer;
+    const bool adam = opt == CFFM_OPT_ADAM;
+    const bool l2 = m->cfg.lamda > 0.f && m->cfg.loss_type == CFFM_LOSS_SQUARE;
+    if (adam) { launch_adam_tick(m->scalars, m->cfg.lr, s); m->launches++; }
+    const float* lr_dev = adam ? m->scalars + 4 : nullptr;
     SparseTables t;
+    t.rowmap = m->rowmap; t.M = m->M;
     int j = 0;
-    if (m->cfg.inner_conv) { t.tab[j] = m->inner_tab; t.acc[j] = m->inner_acc; t.grads[j] = gi; t.K[j] = m->Ki; ++j; }
-    if (m->cfg.outer_conv) { t.tab[j] = m->outer_tab; t.acc[j] = m->outer_acc; t.grads[j] = go; t.K[j] = m->Ko; ++j; }
-    t.tab[j] = m->fbias_tab; t.acc[j] = m->fbias_acc; t.grads[j] = gbr; t.K[j] = 1; ++j;
+    // Adam's sparse apply moves every row; the l2 regulariser makes the two embedding gradients dense (Q9:
+    // the outer table is regularised by lamda_att)
+    if (m->cfg.inner_conv) { t.tab[j] = m->inner_tab; t.acc[j] = m->inner_acc; t.acc2[j] = m->inner_acc2; t.grads[j] = gi; t.K[j] = m->Ki;
+                             t.dense[j] = adam || l2; t.reg[j] = l2 ? m->cfg.lamda : 0.f; ++j; }
+    if (m->cfg.outer_conv) { t.tab[j] = m->outer_tab; t.acc[j] = m->outer_acc; t.acc2[j] = m->outer_acc2; t.grads[j] = go; t.K[j] = m->Ko;
+                             t.dense[j] = adam || l2; t.reg[j] = l2 ? m->cfg.lamda_att : 0.f; ++j; }
+    t.tab[j] = m->fbias_tab; t.acc[j] = m->fbias_acc; t.acc2[j] = m->fbias_acc2; t.grads[j] = gbr; t.K[j] = 1; t.dense[j] = adam; ++j;
+    if (opt == CFFM_OPT_SGD) for (int q = 0; q < 3; ++q) t.acc[q] = nullptr;
     CFFM_PROF(m, "sparse_adagrad", s);
-    launch_sparse_adagrad(&m->sw, t, n_upd, m->cfg.lr, s, &m->launches);
+    launch_sparse_update(&m->sw, t, n_upd, opt, m->cfg.lr, lr_dev, s, &m->launches);
+    // ---- dense update ----
+    CFFM_PROF(m, "dense_adagrad", s);
+    launch_dense_update(m->dense_w, opt == CFFM_OPT_SGD ? nullptr : m->dense_acc, m->dense_acc2, g, L.total, opt, m->cfg.lr, lr_dev, s);
+    m->launches++;
   }
-  // ---- dense update ----
-  { CFFM_PROF(m, "dense_adagrad", s); launch_dense_adagrad(m->dense_w, m->dense_acc, g, L.total, m->cfg.lr, s); }
-  m->launches++;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
 }

@@ -169,7 +169,7 @@ __global__ void k_sumpool(const float* __restrict__ Y, int64_t BH, int H, int P,
 // Head: dense(32), dense(1), beta_outer (CFFM.py:409-414), add_n (:453), prediction and the
 // per-sample loss term / unscaled dLoss/dout (:486-514).  One warp per sample, lane = hidden unit.
 struct HeadArgs {
-  int B, t1_dim, inner_conv, outer_conv, loss_type;
+  int B, t1_dim, inner_conv, outer_conv, loss_type, l2mode;
   const float *t1, *W1, *b1, *W2, *b2, *bias;
   const float *comp_inner, *comp_lin;
   float beta, invB;
@@ -207,7 +207,8 @@ __global__ void k_head_fwd(const HeadArgs a) {
   float term, g;
   const float eps = 1e-7f;
   switch (a.loss_type) {
-    case CFFM_LOSS_SQUARE: term = d * d; g = d; break;                       // :493 (lamda == 0)
+    case CFFM_LOSS_SQUARE:                                                   // :493 (lamda == 0) / :489 l2_loss (lamda > 0)
+      term = a.l2mode ? 0.5f * d * d : d * d; g = d; break;
     case CFFM_LOSS_MSE: term = d * d; g = 2.f * d; break;                    // :506
     case CFFM_LOSS_MAE: term = fabsf(d); g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); break;  // :508
     case CFFM_LOSS_LOG: {                                                    // :496-504
@@ -241,10 +242,12 @@ __global__ void k_loss_sum(const float* __restrict__ terms, int B, float* __rest
 
 // loss value and the scale of dLoss/dout from the (global) loss sum; then gout *= scale.
 __global__ void k_loss_finish(float* __restrict__ scalars, int loss_type, float invB, float* __restrict__ gout,
-                              int B, float* __restrict__ loss_out) {
+                              int B, float* __restrict__ loss_out, float reg_inner, float reg_outer) {
   const float sum = scalars[0];
   float loss, scale;
-  if (loss_type == CFFM_LOSS_SQUARE) { loss = sqrtf(sum * invB + 1e-10f); scale = invB / loss; }
+  if (loss_type == CFFM_LOSS_SQUARE && (reg_inner > 0.f || reg_outer > 0.f)) {  // :489-491: l2_loss + regularisers
+    loss = sum + 0.5f * reg_inner * scalars[6] + 0.5f * reg_outer * scalars[7]; scale = 1.f;
+  } else if (loss_type == CFFM_LOSS_SQUARE) { loss = sqrtf(sum * invB + 1e-10f); scale = invB / loss; }
   else if (loss_type == CFFM_LOSS_HYBRID) { loss = sum; scale = 1.f; }
   else { loss = sum * invB; scale = invB; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,7 +263,10 @@ void launch_loss_sum(Model* m, int B, cudaStream_t s) {
 void launch_loss_finish(Model* m, int B, cudaStream_t s) {
   const float invB = 1.f / (float)((int64_t)B * m->world);
   CFFM_PROF(m, "loss_finish", s);
-  k_loss_finish<<<ceil_div(B, 256), 256, 0, s>>>(m->scalars, m->cfg.loss_type, invB, m->gout, B, m->loss_out);
+  const bool l2 = m->cfg.lamda > 0.f && m->cfg.loss_type == CFFM_LOSS_SQUARE;
+  k_loss_finish<<<ceil_div(B, 256), 256, 0, s>>>(m->scalars, m->cfg.loss_type, invB, m->gout, B, m->loss_out,
+                                                 l2 && m->cfg.inner_conv ? m->cfg.lamda : 0.f,
+                                                 l2 && m->cfg.outer_conv ? m->cfg.lamda_att : 0.f);
   m->launches++;
 }
 
@@ -356,7 +362,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
   {
     HeadArgs a;
     a.B = B; a.t1_dim = m->t1_dim; a.inner_conv = m->cfg.inner_conv; a.outer_conv = m->cfg.outer_conv;
-    a.loss_type = m->cfg.loss_type;
+    a.loss_type = m->cfg.loss_type; a.l2mode = (m->cfg.lamda > 0.f && m->cfg.loss_type == CFFM_LOSS_SQUARE) ? 1 : 0;
     a.t1 = m->t1; a.W1 = w + L.d1_k; a.b1 = w + L.d1_b; a.W2 = w + L.d2_k; a.b2 = w + L.d2_b; a.bias = w + L.bias;
     a.comp_inner = m->comp_inner; a.comp_lin = m->comp_lin; a.beta = m->cfg.beta_outer;
     a.invB = 1.f / (float)((int64_t)B * m->world);

@@ -32,11 +32,20 @@ int sparse_sort_segments(SparseWork* w, const int32_t* ids, int64_t n, int featu
 // segment-sum the gradient rows in order of appearance and apply SparseApplyAdagrad to up to three tables
 struct SparseTables {
   float *tab[3] = {nullptr, nullptr, nullptr};
-  float *acc[3] = {nullptr, nullptr, nullptr};
+  float *acc[3] = {nullptr, nullptr, nullptr};    // slot 1 (Adagrad accumulator / momentum / Adam m); may be null
+  float *acc2[3] = {nullptr, nullptr, nullptr};   // slot 2 (Adam v); may be null
   const float* grads[3] = {nullptr, nullptr, nullptr};
   int K[3] = {0, 0, 0};
+  bool dense[3] = {false, false, false};           // whole-table pass (l2 regulariser / Adam)
+  float reg[3] = {0.f, 0.f, 0.f};                  // regulariser strength of the dense pass
+  int32_t* rowmap = nullptr;                       // [M], -1 = untouched (dense passes only)
+  int64_t M = 0;
 };
-void launch_sparse_adagrad(const SparseWork* w, const SparseTables& t, int64_t n, float lr, cudaStream_t s, int64_t* launches);
-void launch_dense_adagrad(float* w, float* acc, const float* g, int64_t n, float lr, cudaStream_t s);
+void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n, int opt, float lr, const float* lr_dev,
+                          cudaStream_t s, int64_t* launches);
+void launch_dense_update(float* w, float* s1, float* s2, const float* g, int64_t n, int opt, float lr, const float* lr_dev,
+                         cudaStream_t s);
+void launch_adam_tick(float* scalars, float lr, cudaStream_t s);
+void launch_sumsq(const float* x, int64_t n, float* partial512, float* out, cudaStream_t s);
 
 }  // namespace cffm

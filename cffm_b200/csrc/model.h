@@ -59,6 +59,10 @@ struct Model {
   float *inner_tab = nullptr, *outer_tab = nullptr, *fbias_tab = nullptr;
   float *inner_acc = nullptr, *outer_acc = nullptr, *fbias_acc = nullptr;
   float *dense_w = nullptr, *dense_acc = nullptr, *dense_g = nullptr;
+  // second optimizer slot (Adam v) and the row -> segment map of dense table passes (Adam / lamda > 0)
+  float *inner_acc2 = nullptr, *outer_acc2 = nullptr, *fbias_acc2 = nullptr, *dense_acc2 = nullptr;
+  int32_t* rowmap = nullptr;
+  float* sumsq_partial = nullptr;   // [512]
 
   // pair tables
   int *pair_i = nullptr, *pair_j = nullptr;  // [P]

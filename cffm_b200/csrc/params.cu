@@ -46,8 +46,13 @@ int model_build_layout(Model* m) {
   if (c.max_batch < 1) { m->err = "max_batch must be positive"; return CFFM_ERR_INVALID; }
   if (c.activation < 0 || c.activation > CFFM_ACT_GELU) { m->err = "unknown activation"; return CFFM_ERR_INVALID; }
   if (c.loss_type < 0 || c.loss_type > CFFM_LOSS_HYBRID) { m->err = "unknown loss_type"; return CFFM_ERR_INVALID; }
-  if (c.optimizer != CFFM_OPT_ADAGRAD) { m->err = "only AdagradOptimizer is implemented"; return CFFM_ERR_UNSUPPORTED; }
-  if (c.lamda > 0.f) { m->err = "lamda > 0 (dense table regulariser) is not implemented"; return CFFM_ERR_UNSUPPORTED; }
+  if (c.optimizer < 0 || c.optimizer > CFFM_OPT_ADAM) { m->err = "unknown optimizer"; return CFFM_ERR_INVALID; }
+  if (c.lamda > 0.f && c.loss_type != CFFM_LOSS_SQUARE) {
+    // the reference's log_loss + lamda branch indexes variables that do not exist (KeyError);
+    // the other losses ignore lamda
+    if (c.loss_type == CFFM_LOSS_LOG) { m->err = "log_loss with lamda > 0 raises KeyError in the reference"; return CFFM_ERR_UNSUPPORTED; }
+  }
+  if (c.lamda < 0.f) { m->err = "lamda must be >= 0"; return CFFM_ERR_INVALID; }
   if (!(c.lamda_att != 0.f)) { m->err = "lamda_att must be non-zero"; return CFFM_ERR_INVALID; }
   m->conv_depth = 0; m->n_live = 0; m->t1_dim = 0;
   if (c.outer_conv) {
@@ -186,11 +191,17 @@ int model_init_params(Model* m, uint64_t seed) {
     launch_init(m, w + L.d1_k, (int64_t)m->t1_dim * 32, INIT_UNIFORM, sqrtf(6.f / (float)(m->t1_dim + 32)), key(30));  // :409
     launch_init(m, w + L.d2_k, 32, INIT_UNIFORM, sqrtf(6.f / 33.f), key(31));                    // :410
   }
-  // Adagrad slots: initial_accumulator_value = 1e-8 (CFFM.py:523-524)
-  launch_init(m, m->dense_acc, m->lay.total, INIT_CONST, 1e-8f, 0);
-  if (m->inner_acc) launch_init(m, m->inner_acc, M * m->Ki, INIT_CONST, 1e-8f, 0);
-  if (m->outer_acc) launch_init(m, m->outer_acc, M * m->Ko, INIT_CONST, 1e-8f, 0);
-  launch_init(m, m->fbias_acc, M, INIT_CONST, 1e-8f, 0);
+  // optimizer slots: Adagrad initial_accumulator_value = 1e-8 (CFFM.py:523-524); momentum / Adam slots start at 0
+  const float s0 = m->cfg.optimizer == CFFM_OPT_ADAGRAD ? 1e-8f : 0.f;
+  launch_init(m, m->dense_acc, m->lay.total, INIT_CONST, s0, 0);
+  if (m->inner_acc) launch_init(m, m->inner_acc, M * m->Ki, INIT_CONST, s0, 0);
+  if (m->outer_acc) launch_init(m, m->outer_acc, M * m->Ko, INIT_CONST, s0, 0);
+  launch_init(m, m->fbias_acc, M, INIT_CONST, s0, 0);
+  if (m->dense_acc2) launch_init(m, m->dense_acc2, m->lay.total, INIT_CONST, 0.f, 0);
+  if (m->inner_acc2) launch_init(m, m->inner_acc2, M * m->Ki, INIT_CONST, 0.f, 0);
+  if (m->outer_acc2) launch_init(m, m->outer_acc2, M * m->Ko, INIT_CONST, 0.f, 0);
+  if (m->fbias_acc2) launch_init(m, m->fbias_acc2, M, INIT_CONST, 0.f, 0);
+  CFFM_CUDA_OK(m, cudaMemsetAsync(m->scalars, 0, 16 * sizeof(float), m->stream));  // Adam step counter etc.
   CFFM_CUDA_OK(m, cudaGetLastError());
   CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
   return CFFM_OK;
@@ -217,7 +228,18 @@ int model_alloc(Model* m) {
   if (m->cfg.inner_conv) { TRY(dmalloc(m, &m->inner_tab, M * m->Ki)); TRY(dmalloc(m, &m->inner_acc, M * m->Ki)); }
   if (m->cfg.outer_conv) { TRY(dmalloc(m, &m->outer_tab, M * m->Ko)); TRY(dmalloc(m, &m->outer_acc, M * m->Ko)); }
   TRY(dmalloc(m, &m->fbias_tab, M)); TRY(dmalloc(m, &m->fbias_acc, M));
+  if (m->cfg.optimizer == CFFM_OPT_ADAM) {
+    if (m->cfg.inner_conv) TRY(dmalloc(m, &m->inner_acc2, M * m->Ki));
+    if (m->cfg.outer_conv) TRY(dmalloc(m, &m->outer_acc2, M * m->Ko));
+    TRY(dmalloc(m, &m->fbias_acc2, M));
+  }
+  if (m->cfg.optimizer == CFFM_OPT_ADAM || m->cfg.lamda > 0.f) {
+    TRY(dmalloc(m, &m->rowmap, M));
+    CFFM_CUDA_OK(m, cudaMemset(m->rowmap, 0xFF, sizeof(int32_t) * M));  // -1: untouched
+  }
+  TRY(dmalloc(m, &m->sumsq_partial, 512));
   TRY(dmalloc(m, &m->dense_w, m->lay.total)); TRY(dmalloc(m, &m->dense_acc, m->lay.total));
+  if (m->cfg.optimizer == CFFM_OPT_ADAM) TRY(dmalloc(m, &m->dense_acc2, m->lay.total));
   // dense_g = [gradients of the dense block | aux batch sums: q[t1_dim], G, pad[3], rowsums[n_small]]
   m->n_small = 2 * m->F + 6;
   m->aux_off = m->lay.total;
@@ -271,7 +293,7 @@ void model_free(Model* m) {
                  m->hid, m->comp_inner, m->comp_outer, m->comp_lin, m->out, m->pred, m->loss_terms, m->scalars,
                  m->loss_out, m->gout, m->g_inner_rows, m->g_outer_rows, m->g_bias_rows, m->v_head, m->rowbuf,
                  m->partials, m->fb_buf, m->all_ids, m->all_g_inner, m->all_g_outer, m->all_g_bias, m->reduce_descs,
-                 m->eval_acc};
+                 m->eval_acc, m->inner_acc2, m->outer_acc2, m->fbias_acc2, m->dense_acc2, m->rowmap, m->sumsq_partial};
   sparse_work_free(&m->sw);
   tc_free(m);
   void* ds[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
