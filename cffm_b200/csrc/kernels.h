@@ -20,8 +20,8 @@ void launch_loss_finish(Model* m, int B, cudaStream_t s);
 struct SparseWork {
   int64_t cap = 0;
   int32_t *keys_out = nullptr, *vals = nullptr, *vals_out = nullptr, *seg_start = nullptr, *n_uniq = nullptr;
-  uint8_t* flags = nullptr;
-  void* cub_tmp = nullptr;
+  uint8_t* flags = nullptr;       // ping-pong buffers of the radix sort
+  void* cub_tmp = nullptr;        // digit offsets + per-tile segment-head counts
   size_t cub_tmp_bytes = 0;
 };
 int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err);

@@ -1,10 +1,8 @@
 // Optimizer update (CFFM.py:517-529) [TF-1.14]:
 //  - IndexedSlices gradients of the three gathered tables are de-duplicated by a deterministic
-//    sort-by-row + segmented sum (summation in order of appearance, like unique +
+//    (hand-written, stable radix) sort-by-row + segmented sum (summation in order of appearance, like unique +
 //    unsorted_segment_sum) and applied with SparseApplyAdagrad to the touched rows only;
 //  - every other trainable variable gets the dense ApplyAdagrad.  acc0 = 1e-8, no epsilon (Q11).
-#include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 #include <string>
 
 #include "common.cuh"
@@ -17,23 +15,129 @@ __global__ void k_iota(int32_t* v, int64_t n) {
   if (i < n) v[i] = (int32_t)i;
 }
 
-__global__ void k_head_flags(const int32_t* __restrict__ sorted, int64_t n, uint8_t* __restrict__ flags) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1 : 0;
+// ---------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (row id, source position) pairs, 8 bits per pass, hand-written:
+//   k_rs_hist    per-tile digit histograms
+//   k_rs_scan    exclusive scan in (digit, tile) order -> first output slot of every (tile, digit)
+//   k_rs_scatter stable scatter: a tile is walked in rounds of 256 elements; inside a round the rank of
+//                an element among equal digits is popc(match_any & lanes below) + counts of lower warps
+// Equal ids keep their order of appearance, which is what makes the segmented sum below reproduce
+// unique + unsorted_segment_sum's summation order.
+constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void k_rs_hist(const int32_t* __restrict__ keys, int n, int shift, int32_t* __restrict__ hist) {
+  __shared__ int32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int t0 = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int i = t0 + r * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
-static size_t cub_bytes(int64_t cap) {
-  size_t a = 0, b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
-                                  (int32_t*)nullptr, (int)cap, 0, 32);
-  thrust::counting_iterator<int32_t> it(0);
-  cub::DeviceSelect::Flagged(nullptr, b, it, (const uint8_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)cap);
-  return (a > b ? a : b) + 256;
+__global__ void k_rs_scan(int32_t* __restrict__ hist, int ntiles) {  // in place: counts -> first output slots
+  __shared__ int32_t tot[256];
+  const int d = threadIdx.x;
+  int s = 0;
+  for (int b = 0; b < ntiles; ++b) s += hist[b * 256 + d];
+  tot[d] = s;
+  __syncthreads();
+  if (d == 0) { int run = 0; for (int q = 0; q < 256; ++q) { const int c = tot[q]; tot[q] = run; run += c; } }
+  __syncthreads();
+  int run = tot[d];
+  for (int b = 0; b < ntiles; ++b) { const int c = hist[b * 256 + d]; hist[b * 256 + d] = run; run += c; }
+}
+
+__global__ void k_rs_scatter(const int32_t* __restrict__ keys, const int32_t* __restrict__ vals, int n, int shift,
+                             const int32_t* __restrict__ offs, int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+  __shared__ int32_t base[256];
+  __shared__ int32_t wcnt[RS_THREADS / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  base[tid] = offs[blockIdx.x * 256 + tid];
+  const int t0 = blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+#pragma unroll
+    for (int w8 = 0; w8 < RS_THREADS / 32; ++w8) wcnt[w8][tid] = 0;
+    __syncthreads();
+    const int i = t0 + r * RS_THREADS + tid;
+    const bool ok = i < n;
+    const int32_t key = ok ? keys[i] : 0;
+    const int d = ok ? ((key >> shift) & 255) : 256;            // 256: tail lanes, never written
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (ok && rank == 0) wcnt[warp][d] = __popc(peers);
+    __syncthreads();
+    if (ok) {
+      int prior = 0;
+      for (int w8 = 0; w8 < warp; ++w8) prior += wcnt[w8][d];
+      const int dst = base[d] + prior + rank;
+      keys_out[dst] = key;
+      vals_out[dst] = vals[i];
+    }
+    __syncthreads();
+    {
+      int add = 0;
+#pragma unroll
+      for (int w8 = 0; w8 < RS_THREADS / 32; ++w8) add += wcnt[w8][tid];
+      base[tid] += add;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- unique rows: head flags -> exclusive scan -> first sorted position of every segment ----
+__global__ void k_seg_count(const int32_t* __restrict__ sorted, int n, int32_t* __restrict__ tile_heads) {
+  __shared__ int32_t cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int t0 = blockIdx.x * RS_TILE;
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int i = t0 + r * RS_THREADS + threadIdx.x;
+    if (i < n && (i == 0 || sorted[i] != sorted[i - 1])) ++c;
+  }
+  c = (int)warp_sum((float)c);   // <= 2048 per tile: exact in fp32
+  if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_heads[blockIdx.x] = cnt;
+}
+__global__ void k_seg_scan(int32_t* __restrict__ tile_heads, int ntiles, int32_t* __restrict__ n_uniq) {  // one thread: ntiles is small
+  int run = 0;
+  for (int b = 0; b < ntiles; ++b) { const int c = tile_heads[b]; tile_heads[b] = run; run += c; }
+  *n_uniq = run;
+}
+__global__ void k_seg_compact(const int32_t* __restrict__ sorted, int n, const int32_t* __restrict__ tile_off,
+                              int32_t* __restrict__ seg_start) {
+  __shared__ int32_t wtot[RS_THREADS / 32];
+  __shared__ int32_t run;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) run = tile_off[blockIdx.x];
+  __syncthreads();
+  const int t0 = blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int i = t0 + r * RS_THREADS + tid;
+    const bool head = i < n && (i == 0 || sorted[i] != sorted[i - 1]);
+    const unsigned m = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) wtot[warp] = __popc(m);
+    __syncthreads();
+    int prior = run;
+    for (int w8 = 0; w8 < warp; ++w8) prior += wtot[w8];
+    if (head) seg_start[prior + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w8 = 0; w8 < RS_THREADS / 32; ++w8) t += wtot[w8]; run += t; }
+    __syncthreads();
+  }
 }
 
 int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
   w->cap = cap;
-  w->cub_tmp_bytes = cub_bytes(cap);
+  const int64_t ntiles = (cap + RS_TILE - 1) / RS_TILE;
+  w->cub_tmp_bytes = sizeof(int32_t) * (size_t)(ntiles * 256 + ntiles + 16);   // digit offsets + per-tile head counts
   cudaError_t e;
 #define SW_ALLOC(ptr, bytes)                                                        \
   e = cudaMalloc((void**)&(ptr), (bytes));                                           \
@@ -43,7 +147,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
   SW_ALLOC(w->vals_out, sizeof(int32_t) * cap);
   SW_ALLOC(w->seg_start, sizeof(int32_t) * (cap + 1));
   SW_ALLOC(w->n_uniq, sizeof(int32_t) * 4);
-  SW_ALLOC(w->flags, cap);
+  SW_ALLOC(w->flags, sizeof(int32_t) * 2 * cap);   // ping-pong buffers of the sort: keys | values
   SW_ALLOC(w->cub_tmp, w->cub_tmp_bytes);
 #undef SW_ALLOC
   // positions 0..cap-1 never change
@@ -59,18 +163,32 @@ void sparse_work_free(SparseWork* w) {
   *w = SparseWork();
 }
 
-int sparse_sort_segments(SparseWork* w, const int32_t* ids, int64_t n, int features_M, cudaStream_t s, int64_t* launches) {
-  if (n > w->cap) return CFFM_ERR_INVALID;
+int sparse_sort_segments(SparseWork* w, const int32_t* ids, int64_t n64, int features_M, cudaStream_t s, int64_t* launches) {
+  if (n64 > w->cap || n64 < 1) return CFFM_ERR_INVALID;
+  const int n = (int)n64;
   int bits = 1;
   while (bits < 31 && (1ll << bits) < (long long)features_M) ++bits;
-  size_t tmp = w->cub_tmp_bytes;
-  // LSD radix sort is stable: equal ids keep their order of appearance.
-  cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, ids, w->keys_out, w->vals, w->vals_out, (int)n, 0, bits, s);
-  k_head_flags<<<(int)((n + 255) / 256), 256, 0, s>>>(w->keys_out, n, w->flags);
-  thrust::counting_iterator<int32_t> it(0);
-  tmp = w->cub_tmp_bytes;
-  cub::DeviceSelect::Flagged(w->cub_tmp, tmp, it, w->flags, w->seg_start, w->n_uniq, (int)n, s);
-  if (launches) *launches += 5;
+  const int passes = (bits + 7) / 8;
+  const int ntiles = (n + RS_TILE - 1) / RS_TILE;
+  int32_t* offs = reinterpret_cast<int32_t*>(w->cub_tmp);
+  int32_t* tile_heads = offs + (size_t)ntiles * 256;
+  int32_t* tmp_k = reinterpret_cast<int32_t*>(w->flags);
+  int32_t* tmp_v = tmp_k + w->cap;
+  // ping-pong so that the last pass lands in keys_out / vals_out
+  const int32_t* src_k = ids; const int32_t* src_v = w->vals;
+  for (int p = 0; p < passes; ++p) {
+    const bool to_out = ((passes - 1 - p) % 2) == 0;
+    int32_t* dst_k = to_out ? w->keys_out : tmp_k;
+    int32_t* dst_v = to_out ? w->vals_out : tmp_v;
+    k_rs_hist<<<ntiles, RS_THREADS, 0, s>>>(src_k, n, 8 * p, offs);
+    k_rs_scan<<<1, 256, 0, s>>>(offs, ntiles);
+    k_rs_scatter<<<ntiles, RS_THREADS, 0, s>>>(src_k, src_v, n, 8 * p, offs, dst_k, dst_v);
+    src_k = dst_k; src_v = dst_v;
+  }
+  k_seg_count<<<ntiles, RS_THREADS, 0, s>>>(w->keys_out, n, tile_heads);
+  k_seg_scan<<<1, 1, 0, s>>>(tile_heads, ntiles, w->n_uniq);
+  k_seg_compact<<<ntiles, RS_THREADS, 0, s>>>(w->keys_out, n, tile_heads, w->seg_start);
+  if (launches) *launches += 3 * passes + 3;
   return cudaGetLastError() == cudaSuccess ? CFFM_OK : CFFM_ERR_CUDA;
 }
 
