@@ -555,24 +555,38 @@ __global__ void k_wgrad_reduce(const float* __restrict__ partial, int n_split, i
   }
 }
 
-// d b_l[q] = sum_m dY_l[m, q]: chunk partials over the rows, then the chunks in order
-__global__ void k_colsum_bf16(const bf16* __restrict__ X, int64_t rows, int ld, int n, float* __restrict__ partial, int C) {
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
-  const int c = blockIdx.y;
+// d b_l[q] = sum_m dY_l[m, q]: chunk partials over the rows, then the chunks in order.
+// A thread owns 8 adjacent channels (one 16-byte load per row) and every R-th row of the chunk; the R
+// row lanes are combined through shared memory in a fixed order.  blockDim = (Pp/8) * R.
+__global__ void k_colsum_bf16(const bf16* __restrict__ X, int64_t rows, int Pp, int n, float* __restrict__ partial, int C) {
+  extern __shared__ float red[];               // [R][Pp]
+  const int CG = Pp >> 3;
+  const int R = blockDim.x / CG;
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+  const int c = blockIdx.x;
   const int64_t rpc = (rows + C - 1) / C;
   const int64_t r0 = (int64_t)c * rpc;
   const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
-  float s = 0.f;
-  if (col < n)
-    for (int64_t r = r0 + warp; r < r1; r += 8) s += __bfloat162float(X[r * ld + col]);
-  red[warp][lane] = s;
-  __syncthreads();
-  if (warp == 0 && col < n) {
-    float t = 0.f;
+  float acc[8];
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][lane];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < R) {
+    for (int64_t r = r0 + rl; r < r1; r += R) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * Pp) + cg);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(wv[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * Pp + cg * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < n; col += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < R; ++q) t += red[q * Pp + col];
     partial[(int64_t)c * n + col] = t;
   }
 }
@@ -661,7 +675,7 @@ int tc_alloc(Model* m, bool train) {
     int max_split = (2 * 148 + tiles - 1) / tiles; if (max_split < 1) max_split = 1;
     st->wg_partial_floats = (int64_t)max_split * 4 * Pp * Pp;
     TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
-    TCTRY(tcmalloc(m, &st->bg_partial, 64 * (int64_t)m->P));
+    TCTRY(tcmalloc(m, &st->bg_partial, 2 * 148 * (int64_t)m->P));
   }
   return CFFM_OK;
 }
@@ -789,9 +803,10 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
     const int64_t rows = gm.M;
     {  // bias gradient
       CFFM_PROF(m, "colsum", s);
-      const int C = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));
-      dim3 grid(ceil_div(P, 32), C);
-      k_colsum_bf16<<<grid, 256, 0, s>>>(st->dY[l], rows, Pp, P, st->bg_partial, C);
+      const int C = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
+      const int CG = Pp / 8;
+      int R = 512 / CG; if (R < 1) R = 1; if (R > 32) R = 32;
+      k_colsum_bf16<<<C, CG * R, sizeof(float) * R * Pp, s>>>(st->dY[l], rows, Pp, P, st->bg_partial, C);
       k_sum_chunks<<<ceil_div(P, 128), 128, 0, s>>>(st->bg_partial, P, C, g + m->lay.conv_b[l]);
       m->launches += 2;
     }

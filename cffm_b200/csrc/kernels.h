@@ -22,6 +22,8 @@ struct SparseWork {
   int32_t *keys_out = nullptr, *vals = nullptr, *vals_out = nullptr, *seg_start = nullptr, *n_uniq = nullptr;
   uint8_t* flags = nullptr;       // ping-pong buffers of the radix sort
   void* cub_tmp = nullptr;        // digit offsets + per-tile segment-head counts
+  float* pieces = nullptr;        // partial sums of segment pieces that cross chunk borders
+  int32_t* chunk_flags = nullptr;
   size_t cub_tmp_bytes = 0;
 };
 int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err);

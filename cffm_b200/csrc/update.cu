@@ -24,6 +24,8 @@ __global__ void k_iota(int32_t* v, int64_t n) {
 // Equal ids keep their order of appearance, which is what makes the segmented sum below reproduce
 // unique + unsorted_segment_sum's summation order.
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int SEG_LT = 128;          // entries per chunk of the segmented reduction
+constexpr int SEG_MAXC = 2;          // columns per lane and table (K <= 64)
 
 __global__ void k_rs_hist(const int32_t* __restrict__ keys, int n, int shift, int32_t* __restrict__ hist) {
   __shared__ int32_t h[256];
@@ -149,6 +151,11 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
   SW_ALLOC(w->n_uniq, sizeof(int32_t) * 4);
   SW_ALLOC(w->flags, sizeof(int32_t) * 2 * cap);   // ping-pong buffers of the sort: keys | values
   SW_ALLOC(w->cub_tmp, w->cub_tmp_bytes);
+  {
+    const int64_t chunks = (cap + SEG_LT - 1) / SEG_LT + 1;
+    SW_ALLOC(w->pieces, sizeof(float) * chunks * 2 * 3 * SEG_MAXC * 32);
+    SW_ALLOC(w->chunk_flags, sizeof(int32_t) * chunks);
+  }
 #undef SW_ALLOC
   // positions 0..cap-1 never change
   k_iota<<<(int)((cap + 255) / 256), 256>>>(w->vals, cap);
@@ -158,7 +165,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
 }
 
 void sparse_work_free(SparseWork* w) {
-  void* p[] = {w->keys_out, w->vals, w->vals_out, w->seg_start, w->n_uniq, w->flags, w->cub_tmp};
+  void* p[] = {w->keys_out, w->vals, w->vals_out, w->seg_start, w->n_uniq, w->flags, w->cub_tmp, w->pieces, w->chunk_flags};
   for (void* q : p) if (q) cudaFree(q);
   *w = SparseWork();
 }
@@ -224,33 +231,115 @@ __device__ __forceinline__ float seg_sum(const float* __restrict__ grads, int K,
   return g;
 }
 
-// One warp per unique row: IndexedSlices de-duplication + SparseApply* on the touched rows only.
-__global__ void k_sparse_update(const int32_t* __restrict__ sorted_ids, const int32_t* __restrict__ pos,
-                                const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n,
-                                SparseTables t, int opt, float lr, const float* __restrict__ lr_dev) {
-  const int lane = threadIdx.x & 31;
-  const int U = *n_uniq;
-  if (lr_dev) lr = *lr_dev;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < U; sgm += nwarps) {
-    const int start = seg_start[sgm];
-    const int end = (sgm + 1 < U) ? seg_start[sgm + 1] : n;
-    const int64_t row = sorted_ids[start];
+// IndexedSlices de-duplication + SparseApply* on the touched rows only, as a chunked segmented
+// reduction: the sorted list is cut into chunks of SEG_LT entries, one warp per chunk adds the gradient
+// rows of every segment piece inside its chunk in order of appearance (lane = column).  A segment that
+// lies inside one chunk is applied at once; pieces of segments that cross chunk borders go to scratch and
+// k_seg_fixup adds them up, chunk after chunk, from the chunk the segment starts in.  Heavily duplicated
+// rows (one id in 20-95 % of a batch) no longer serialise on a single warp, and the
+// summation order is a fixed function of the sorted list: the update is deterministic.
+struct SegAcc { float v[3][SEG_MAXC]; };
+
+__device__ __forceinline__ void seg_acc_zero(SegAcc& a) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (!t.tab[j] || t.dense[j]) continue;
-      const int K = t.K[j];
-      for (int k = lane; k < K; k += 32) {
-        const float g = seg_sum(t.grads[j], K, k, pos, start, end);
-        const int64_t o = row * K + k;
-        float w = t.tab[j][o], s1 = t.acc[j] ? t.acc[j][o] : 0.f, s2 = t.acc2[j] ? t.acc2[j][o] : 0.f;
-        opt_apply(opt, w, s1, s2, g, lr);
-        t.tab[j][o] = w;
-        if (t.acc[j]) t.acc[j][o] = s1;
-        if (t.acc2[j]) t.acc2[j][o] = s2;
-      }
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < SEG_MAXC; ++c) a.v[j][c] = 0.f;
+}
+__device__ __forceinline__ void seg_acc_row(SegAcc& a, const SparseTables& t, int64_t p, int lane) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (!t.tab[j] || t.dense[j]) continue;
+#pragma unroll
+    for (int c = 0; c < SEG_MAXC; ++c) {
+      const int k = lane + 32 * c;
+      if (k < t.K[j]) a.v[j][c] += __ldg(t.grads[j] + p * t.K[j] + k);
     }
   }
+}
+__device__ __forceinline__ void seg_acc_apply(const SegAcc& a, const SparseTables& t, int64_t row, int lane, int opt, float lr) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (!t.tab[j] || t.dense[j]) continue;
+#pragma unroll
+    for (int c = 0; c < SEG_MAXC; ++c) {
+      const int k = lane + 32 * c;
+      if (k >= t.K[j]) continue;
+      const int64_t o = row * t.K[j] + k;
+      float w = t.tab[j][o], s1 = t.acc[j] ? t.acc[j][o] : 0.f, s2 = t.acc2[j] ? t.acc2[j][o] : 0.f;
+      opt_apply(opt, w, s1, s2, a.v[j][c], lr);
+      t.tab[j][o] = w;
+      if (t.acc[j]) t.acc[j][o] = s1;
+      if (t.acc2[j]) t.acc2[j][o] = s2;
+    }
+  }
+}
+// piece scratch: [chunk][slot 0/1][table][SEG_MAXC][32 lanes]
+__device__ __forceinline__ float* piece_ptr(float* pieces, int chunk, int slot) { return pieces + ((int64_t)chunk * 2 + slot) * (3 * SEG_MAXC * 32); }
+__device__ __forceinline__ void seg_acc_store(const SegAcc& a, float* p, int lane) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < SEG_MAXC; ++c) p[(j * SEG_MAXC + c) * 32 + lane] = a.v[j][c];
+}
+__device__ __forceinline__ void seg_acc_add(SegAcc& a, const float* p, int lane) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < SEG_MAXC; ++c) a.v[j][c] += p[(j * SEG_MAXC + c) * 32 + lane];
+}
+
+// flags[chunk]: bit0 = slot 1 holds the open tail piece of a segment that starts in this chunk;
+//               bit1 = slot 0 holds a middle piece (the segment covers the whole chunk and goes on)
+__global__ void k_seg_chunks(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, int n, SparseTables t, int opt,
+                             float lr, const float* __restrict__ lr_dev, float* __restrict__ pieces, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int t0 = chunk * SEG_LT;
+  if (t0 >= n) return;
+  if (lr_dev) lr = *lr_dev;
+  const int t1 = min(n, t0 + SEG_LT);
+  const bool head_open = t0 > 0 && sorted[t0 - 1] == sorted[t0];
+  int fl = 0;
+  SegAcc acc; seg_acc_zero(acc);
+  bool first_piece = true;
+  int key = sorted[t0];
+  for (int tt = t0; tt < t1; ++tt) {
+    seg_acc_row(acc, t, (int64_t)pos[tt], lane);
+    const bool last_in_chunk = tt + 1 == t1;
+    const int nxt = (tt + 1 < n) ? sorted[tt + 1] : -1;
+    if (last_in_chunk || nxt != key) {
+      const bool closes = nxt != key;                          // the segment ends with this entry
+      const bool started_inside = !(first_piece && head_open);
+      if (started_inside && closes) seg_acc_apply(acc, t, key, lane, opt, lr);
+      else if (!started_inside && closes) seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane);
+      else if (started_inside && !closes) { seg_acc_store(acc, piece_ptr(pieces, chunk, 1), lane); fl |= 1; }
+      else { seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane); fl |= 2; }
+      seg_acc_zero(acc);
+      first_piece = false;
+      key = nxt;
+    }
+  }
+  if (lane == 0) flags[chunk] = fl;
+}
+
+__global__ void k_seg_fixup(const int32_t* __restrict__ sorted, int n, SparseTables t, int opt, float lr,
+                            const float* __restrict__ lr_dev, const float* __restrict__ pieces, const int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int t0 = chunk * SEG_LT;
+  if (t0 >= n) return;
+  if (!(flags[chunk] & 1)) return;                              // no segment starts here and runs on
+  if (lr_dev) lr = *lr_dev;
+  const int t1 = min(n, t0 + SEG_LT);
+  const int key = sorted[t1 - 1];
+  SegAcc acc; seg_acc_zero(acc);
+  seg_acc_add(acc, piece_ptr(const_cast<float*>(pieces), chunk, 1), lane);
+  for (int cc = chunk + 1;; ++cc) {                            // the pieces of the following chunks, in order
+    seg_acc_add(acc, piece_ptr(const_cast<float*>(pieces), cc, 0), lane);
+    if (!(flags[cc] & 2)) break;                               // a first piece: the segment ends inside chunk cc
+  }
+  seg_acc_apply(acc, t, key, lane, opt, lr);
 }
 
 // rowmap[row] = segment index for the touched rows (reset to -1 afterwards)
@@ -296,10 +385,11 @@ void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n,
   bool any_sparse = false, any_dense = false;
   for (int j = 0; j < 3; ++j) if (t.tab[j]) { if (t.dense[j]) any_dense = true; else any_sparse = true; }
   if (any_sparse) {
-    int blocks = (int)((n * 32 + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_sparse_update<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
-    if (launches) *launches += 1;
+    const int chunks = (int)((n + SEG_LT - 1) / SEG_LT);
+    const int blocks = (chunks * 32 + 255) / 256;
+    k_seg_chunks<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, (int)n, t, opt, lr, lr_dev, w->pieces, w->chunk_flags);
+    k_seg_fixup<<<blocks, 256, 0, s>>>(w->keys_out, (int)n, t, opt, lr, lr_dev, w->pieces, w->chunk_flags);
+    if (launches) *launches += 2;
   }
   if (any_dense) {
     int ub = (int)((n + 255) / 256); if (ub > 148 * 4) ub = 148 * 4;
