@@ -304,20 +304,40 @@ __global__ void k_seg_chunks(const int32_t* __restrict__ sorted, const int32_t* 
   SegAcc acc; seg_acc_zero(acc);
   bool first_piece = true;
   int key = sorted[t0];
-  for (int tt = t0; tt < t1; ++tt) {
-    seg_acc_row(acc, t, (int64_t)pos[tt], lane);
-    const bool last_in_chunk = tt + 1 == t1;
-    const int nxt = (tt + 1 < n) ? sorted[tt + 1] : -1;
-    if (last_in_chunk || nxt != key) {
-      const bool closes = nxt != key;                          // the segment ends with this entry
-      const bool started_inside = !(first_piece && head_open);
-      if (started_inside && closes) seg_acc_apply(acc, t, key, lane, opt, lr);
-      else if (!started_inside && closes) seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane);
-      else if (started_inside && !closes) { seg_acc_store(acc, piece_ptr(pieces, chunk, 1), lane); fl |= 1; }
-      else { seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane); fl |= 2; }
-      seg_acc_zero(acc);
-      first_piece = false;
-      key = nxt;
+  // four entries per trip: their positions, keys and gradient rows are loaded before any is added
+  for (int tb = t0; tb < t1; tb += 4) {
+    int pp[4], kk[5];
+    SegAcc rows4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tt = tb + u;
+      pp[u] = tt < t1 ? pos[tt] : 0;
+      kk[u] = tt < n ? sorted[tt] : -1;
+    }
+    kk[4] = tb + 4 < n ? sorted[tb + 4] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { seg_acc_zero(rows4[u]); if (tb + u < t1) seg_acc_row(rows4[u], t, (int64_t)pp[u], lane); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int tt = tb + u;
+      if (tt >= t1) break;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows4[u].v[j][c];
+      const bool last_in_chunk = tt + 1 == t1;
+      const int nxt = kk[u + 1];
+      if (last_in_chunk || nxt != key) {
+        const bool closes = nxt != key;                          // the segment ends with this entry
+        const bool started_inside = !(first_piece && head_open);
+        if (started_inside && closes) seg_acc_apply(acc, t, key, lane, opt, lr);
+        else if (!started_inside && closes) seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane);
+        else if (started_inside && !closes) { seg_acc_store(acc, piece_ptr(pieces, chunk, 1), lane); fl |= 1; }
+        else { seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane); fl |= 2; }
+        seg_acc_zero(acc);
+        first_piece = false;
+        key = nxt;
+      }
     }
   }
   if (lane == 0) flags[chunk] = fl;

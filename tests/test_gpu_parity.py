@@ -219,7 +219,7 @@ def test_gather_is_bit_exact():
 
 def test_sparse_adagrad_operator():
     """Sort-by-row + segmented sum + SparseApplyAdagrad: unique rows bit exact, untouched rows
-    bitwise unchanged, touched rows equal to the in-order fp32 restatement."""
+    bitwise unchanged, touched rows equal to the fp32 restatement of the kernel's (deterministic) summation order."""
     from cffm_b200 import _lib
     import ctypes as C
     lib = _lib.load()
@@ -242,9 +242,16 @@ def test_sparse_adagrad_operator():
     uniq = np.unique(ids)
     assert int(nu_d.item()) == len(uniq)
     assert np.array_equal(u_d[: len(uniq)].cpu().numpy(), uniq)
+    # the kernel's summation order, restated: the stably sorted list is cut into chunks of 128 entries; inside a
+    # chunk a row's gradient rows are added in order of appearance, then the chunk pieces in chunk order (fp32)
+    order = np.argsort(ids, kind="stable")
+    pieces = {}
+    for t, src in enumerate(order):
+        key = (int(ids[src]), t // 128)
+        pieces[key] = pieces.get(key, np.zeros(K, dtype=np.float32)) + grads[src]
     G = np.zeros((M, K), dtype=np.float32)
-    for i in range(n):  # fp32, in order of appearance
-        G[ids[i]] += grads[i]
+    for (row, chunk) in sorted(pieces):
+        G[row] = G[row] + pieces[(row, chunk)]
     a_want = acc + G * G
     w_want = tab - lr * G / np.sqrt(a_want)
     got_w, got_a = t_d.cpu().numpy(), a_d.cpu().numpy()
