@@ -53,6 +53,9 @@ template <int ACT, bool L0>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
   static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
+  // layer 0: the synthesised cube slab goes to tensor memory (tcgen05.st) and the MMA reads A from there:
+  // the kernel was bound by shared-memory bandwidth (STS of the slab + UMMA reads of A and B + LDS of the rows)
+  static constexpr bool kATmem = L0;
   CUtensorMap mapA, mapB;
   Geom g;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
@@ -91,10 +94,11 @@ struct ConvFwdTC : KMajorA, KMajorB {
     for (int e = t; e < g.Pp; e += 256)
       tab[e] = e < g.P ? ((uint32_t)(pair_i[e] * g.K * 4) | ((uint32_t)(pair_j[e] * g.K * 4) << 16)) : (zero_row | (zero_row << 16));
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex, SynthState&) const {
+  // 8 pairs x 4 taps = 32 bf16 = 16 packed columns of this thread's row (columns half*16 .. +15 of the stage)
+  __device__ void synth_regs(uint32_t (&pk)[16], Unit un, int kc, int t256, const uint8_t* ex) const {
     const uint8_t* o = ex;
     const uint32_t* tab = reinterpret_cast<const uint32_t*>(ex + (g.F + 1) * g.K * 4);
-    const int t = t256 & 127, half = t256 >> 7;   // row of the stage; which 4 of its 8 16-byte chunks
+    const int t = t256 & 127, half = t256 >> 7;
     const int m = un.m_tile * BM + t;
     const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
     const uint8_t* oh = o + 8 * h;
@@ -102,19 +106,29 @@ struct ConvFwdTC : KMajorA, KMajorB {
     const uint4* te = reinterpret_cast<const uint4*>(tab + kc * 16 + half * 8);
     const uint4 e0 = te[0], e1 = te[1];
     const uint32_t ent[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    uint32_t cur_i = 0xFFFFFFFFu;
+    float2 oi = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t en = ent[c4 * 2 + hf];
-        const float2 oi = *reinterpret_cast<const float2*>(oh + (en & 0xFFFFu));
-        const float2 oj = *reinterpret_cast<const float2*>(ow + (en >> 16));
-        pk[hf * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
-        pk[hf * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
-      }
-      *reinterpret_cast<uint4*>(sA + sw128_offset(t, half * 4 + c4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    for (int pr = 0; pr < 8; ++pr) {
+      const uint32_t en = ent[pr];
+      if ((en & 0xFFFFu) != cur_i) { cur_i = en & 0xFFFFu; oi = *reinterpret_cast<const float2*>(oh + cur_i); }  // uniform: pairs run i-major
+      const float2 oj = *reinterpret_cast<const float2*>(ow + (en >> 16));
+      pk[pr * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
+      pk[pr * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
     }
+  }
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex, SynthState&) const {
+    uint32_t pk[16];
+    synth_regs(pk, un, kc, t256, ex);
+    const int t = t256 & 127, half = t256 >> 7;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+      *reinterpret_cast<uint4*>(sA + sw128_offset(t, half * 4 + c4)) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+  }
+  __device__ void synth_a_tmem(uint32_t taddr, Unit un, int kc, int t256, const uint8_t* ex, SynthState&) const {
+    uint32_t pk[16];
+    synth_regs(pk, un, kc, t256, ex);
+    tmem_st16(taddr + (uint32_t)((t256 >> 7) * 16), pk);
   }
   struct Epilogue {
     const ConvFwdTC& p; int row; float rowsum;
@@ -161,6 +175,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
   // the reduction is short (Pp/64 stages per tile) and the epilogue waits on global loads of the mask:
   // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks) keep up with the MMA
   static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
+  static constexpr bool kATmem = false;
   CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
@@ -225,6 +240,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   static constexpr int kStages = 3, kExtraBytes = 72 * 1024, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
+  static constexpr bool kATmem = false;
   CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // Ho = 16: 256 rows per sample
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
@@ -412,6 +428,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
   // their accumulators sit side by side in TMEM (2 x 256 columns, one buffer: the units are long)
   static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2, kEpiWarps = 4;
+  static constexpr bool kATmem = false;
   static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
   static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
   CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
@@ -758,10 +775,13 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     const int m_tiles = (g.M + BM - 1) / BM;
     if (l == 0) {
       ConvFwdTC<ACT, true> p;
-      p.g = g; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
+      Geom g0 = g;   // two accumulator buffers + four A stages share the 512 TMEM columns: N <= 192
+      g0.BN = 64; for (int bn = 192; bn > 64; bn -= 64) if (Pp % bn == 0) { g0.BN = bn; break; }
+      g0.tiles_n = Pp / g0.BN;
+      p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
       memset(&p.mapA, 0, sizeof(p.mapA));
-      TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g.BN, 64));
+      TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g0.BN, 64));
       TCTRY(launch_tc(m, p, m_tiles, s));
     } else {
       ConvFwdTC<ACT, false> p;

@@ -34,7 +34,7 @@ constexpr int CTL_BYTES = (sizeof(Ctl) + 63) & ~63;
 // dynamic shared memory of a policy: 1 KB alignment slack + stages + control block + policy scratch
 template <class P>
 constexpr size_t smem_bytes() {
-  return 1024 + (size_t)P::kStages * (P::kATiles * A_STAGE_BYTES + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
+  return 1024 + (size_t)P::kStages * ((P::kATmem ? 0 : P::kATiles * A_STAGE_BYTES) + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
 }
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int cols) {
@@ -63,6 +63,8 @@ struct MNMajorB {
 //   static constexpr bool kSynthA
 //   static constexpr int kStages, kExtraBytes (policy scratch; the second half belongs to the synth warps)
 //   static constexpr int kEpiWarps (4, or 8: two warps per TMEM lane quarter taking alternate 32-column chunks),
+//   static constexpr bool kATmem (kSynthA only: the producers write the A stage into tensor memory with tcgen05.st
+//                        and the MMA reads it from there -- no shared-memory traffic for A; 32 columns per stage),
 //   static constexpr int kATiles (128-row A tiles that share one B stage: accumulators side by side in TMEM),
 //                        kAccBufs (1 or 2 accumulator buffers; kAccBufs * kATiles * bn() <= 512 columns)
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   constexpr int STAGES = P::kStages;
-  constexpr int A_BYTES = P::kATiles * A_STAGE_BYTES;
+  constexpr int A_BYTES = P::kATmem ? 0 : P::kATiles * A_STAGE_BYTES;
+  constexpr int A_TMEM_COLS = BK / 2;        // one stage of A in tensor memory: 64 bf16 per row = 32 columns
   uint8_t* sB = sA + STAGES * A_BYTES;
   Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_STAGE_BYTES_MAX);
   uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + CTL_BYTES;
@@ -92,7 +95,8 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   const int lane = threadIdx.x & 31;
   const int BN = prm.bn();
   const int ACC_COLS = P::kATiles * BN;      // TMEM columns of one accumulator buffer
-  const uint32_t ncols = tmem_cols_for(P::kAccBufs * ACC_COLS);
+  const int A_TMEM_BASE = P::kAccBufs * ACC_COLS;   // first column of the A stages (kATmem)
+  const uint32_t ncols = tmem_cols_for(P::kAccBufs * ACC_COLS + (P::kATmem ? STAGES * A_TMEM_COLS : 0));
   const int n_iters = prm.n_iters((int)blockIdx.x, (int)gridDim.x);
 
   if (warp == 0 && lane == 0) prm.prefetch();
@@ -138,12 +142,19 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES_MAX);
-#pragma unroll
-          for (int at = 0; at < P::kATiles; ++at)
+          if constexpr (P::kATmem) {
+            const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(d_tmem + (uint32_t)(at * BN), prm.a_desc(a_addr + at * A_STAGE_BYTES, k), prm.b_desc(b_addr, k), idesc,
-                        (kc | k) != 0);
+              umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(k * (UMMA_K / 2)), prm.b_desc(b_addr, k), idesc, (kc | k) != 0);
+          } else {
+#pragma unroll
+            for (int at = 0; at < P::kATiles; ++at)
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d_tmem + (uint32_t)(at * BN), prm.a_desc(a_addr + at * A_STAGE_BYTES, k), prm.b_desc(b_addr, k), idesc,
+                          (kc | k) != 0);
+          }
           umma_commit(&ctl->empty[stage]);              // frees the smem stage when these MMAs retire
           if (kc == KC - 1) umma_commit(&ctl->tfull[buf]);  // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -181,7 +192,8 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   } else {
     // ------------------------------------------------------------------ A synthesis (kSynthA only)
     if constexpr (P::kSynthA) {
-      const int t = (warp - 2 - P::kEpiWarps) * 32 + lane;  // 256 producer threads
+      // 256 producer threads: row = TMEM lane quarter of this warp * 32 + lane, half = which group of four warps
+      const int t = (((warp - 2 - P::kEpiWarps) >> 2) << 7) + (warp & 3) * 32 + lane;
       typename P::SynthState sst;            // per-thread producer state that lives across stages
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iters; ++it) {
@@ -192,8 +204,15 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          prm.synth_a(sA + stage * A_BYTES, un, kc, t, extra_synth, sst);
-          fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core
+          if constexpr (P::kATmem) {
+            const uint32_t ta = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS) + ((uint32_t)((warp & 3) * 32) << 16);
+            prm.synth_a_tmem(ta, un, kc, t, extra_synth, sst);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            prm.synth_a(sA + stage * A_BYTES, un, kc, t, extra_synth, sst);
+            fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
