@@ -52,10 +52,11 @@ __device__ __forceinline__ float phi_scale() { return ACT == CFFM_ACT_SELU ? kSe
 template <int ACT, bool L0>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
-  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = L0 ? 8 : 4;
   // layer 0: the synthesised cube slab goes to tensor memory (tcgen05.st) and the MMA reads A from there:
   // the kernel was bound by shared-memory bandwidth (STS of the slab + UMMA reads of A and B + LDS of the rows)
-  static constexpr bool kATmem = L0;
+  // ... and every slab feeds two N tiles (kBPair): the producers, not the tensor pipe, bounded the kernel
+  static constexpr bool kATmem = L0, kSynthAlternate = L0, kBPair = L0;
   CUtensorMap mapA, mapB;
   Geom g;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
@@ -65,11 +66,12 @@ struct ConvFwdTC : KMajorA, KMajorB {
   __device__ int m_tiles() const { return (g.M + BM - 1) / BM; }
   __device__ int n_iters(int cta, int ncta) const {
     const int mt = m_tiles();
-    return (cta < mt ? (mt - cta + ncta - 1) / ncta : 0) * g.tiles_n;
+    return (cta < mt ? (mt - cta + ncta - 1) / ncta : 0) * units_n();
   }
-  __device__ Unit unit(int cta, int ncta, int it) const { return {cta + (it / g.tiles_n) * ncta, it % g.tiles_n, 0}; }
+  __device__ int units_n() const { return L0 ? g.tiles_n >> 1 : g.tiles_n; }   // layer 0: a unit = two N tiles
+  __device__ Unit unit(int cta, int ncta, int it) const { return {cta + (it / units_n()) * ncta, it % units_n(), 0}; }
   __device__ int k_chunks(Unit) const { return 4 * g.Pp / BK; }
-  __device__ uint32_t tx_bytes() const { return (uint32_t)((L0 ? 0 : A_STAGE_BYTES) + g.BN * BK * 2); }
+  __device__ uint32_t tx_bytes() const { return (uint32_t)(L0 ? 2 * g.BN * BK * 2 : A_STAGE_BYTES + g.BN * BK * 2); }
   __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
     const int m0 = un.m_tile * BM;
@@ -131,17 +133,41 @@ struct ConvFwdTC : KMajorA, KMajorB {
     tmem_st16(taddr + (uint32_t)((t256 >> 7) * 16), pk);
   }
   struct Epilogue {
-    const ConvFwdTC& p; int row; float rowsum;
-    __device__ Epilogue(const ConvFwdTC& p_, uint8_t*, int row_, int) : p(p_), row(row_), rowsum(0.f) {}
-    __device__ void begin(Unit un) { if (un.n_tile == 0) rowsum = 0.f; }
+    // layer 0: even N tiles belong to epilogue warps 0..3, odd ones to warps 4..7; the two partial
+    // row sums meet in shared memory (double-buffered on the M tile's parity)
+    // The accumulators of a unit are not double-buffered there, so the drain is on the critical path:
+    // the bias sits in shared memory (zero beyond P: no per-element guards, broadcast LDS.128).
+    const ConvFwdTC& p; int row, ew; float rowsum; float* xch; const float* sbias; int flip;
+    __device__ Epilogue(const ConvFwdTC& p_, uint8_t* ex, int row_, int ew_)
+        : p(p_), row(row_), ew(ew_), rowsum(0.f), xch(reinterpret_cast<float*>(ex)), sbias(xch + 2 * BM), flip(0) {
+      if (L0) {
+        float* sb = xch + 2 * BM;
+        const int ncol = p.g.tiles_n * p.g.BN;
+        for (int e = ew * 32 + (threadIdx.x & 31); e < ncol; e += 256) sb[e] = e < p.g.P ? __ldg(p.bias + e) : 0.f;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+    __device__ void begin(Unit un) { if (un.n_tile < (L0 ? 2 : 1)) rowsum = 0.f; }
     __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
       const int m = un.m_tile * BM + row;
       const int n0 = un.n_tile * p.g.BN + c0;
+      if (L0 && n0 >= p.g.Pp) return;     // N tiles may overhang the padded channel count (zero weights)
       uint32_t pk[16];
+      float bv[32];
+      if (L0) {
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + n0 + 4 * q4);
+          bv[4 * q4] = b4.x; bv[4 * q4 + 1] = b4.y; bv[4 * q4 + 2] = b4.z; bv[4 * q4 + 3] = b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bv[j] = n0 + j < p.g.P ? __ldg(p.bias + n0 + j) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float y0 = v[j] + (n0 + j < p.g.P ? __ldg(p.bias + n0 + j) : 0.f);
-        const float y1 = v[j + 1] + (n0 + j + 1 < p.g.P ? __ldg(p.bias + n0 + j + 1) : 0.f);
+        const float y0 = v[j] + bv[j];
+        const float y1 = v[j + 1] + bv[j + 1];
         const float x0 = phi_f<ACT>(y0), x1 = phi_f<ACT>(y1);
         rowsum += x0 + x1;
         pk[j >> 1] = pack2(x0, x1);
@@ -153,10 +179,18 @@ struct ConvFwdTC : KMajorA, KMajorB {
       }
     }
     __device__ void end(Unit un) {
-      if (un.n_tile != p.g.tiles_n - 1) return;
+      if (un.n_tile < p.g.tiles_n - (L0 ? 2 : 1)) return;
       const int m = un.m_tile * BM + row;
       float s = m < p.g.M ? rowsum : 0.f;
       for (int off = p.g.Ho >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (L0) {
+        float* slot = xch + flip * BM + row;
+        flip ^= 1;
+        if (ew >= 4) *slot = s;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (ew >= 4) return;
+        s += *slot;
+      }
       int b, h, w; p.g.pos(m, b, h, w);
       if (w == 0 && m < p.g.M) p.t1[(int64_t)b * p.t1_dim + p.sp_off + h] = s;
     }
@@ -175,7 +209,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
   // the reduction is short (Pp/64 stages per tile) and the epilogue waits on global loads of the mask:
   // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks) keep up with the MMA
   static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
-  static constexpr bool kATmem = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
   CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
@@ -240,7 +274,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   static constexpr int kStages = 3, kExtraBytes = 72 * 1024, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
-  static constexpr bool kATmem = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
   CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // Ho = 16: 256 rows per sample
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
@@ -428,7 +462,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
   // their accumulators sit side by side in TMEM (2 x 256 columns, one buffer: the units are long)
   static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2, kEpiWarps = 4;
-  static constexpr bool kATmem = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
   static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
   static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
   CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
@@ -775,9 +809,15 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     const int m_tiles = (g.M + BM - 1) / BM;
     if (l == 0) {
       ConvFwdTC<ACT, true> p;
-      Geom g0 = g;   // two accumulator buffers + four A stages share the 512 TMEM columns: N <= 192
-      g0.BN = 64; for (int bn = 192; bn > 64; bn -= 64) if (Pp % bn == 0) { g0.BN = bn; break; }
-      g0.tiles_n = Pp / g0.BN;
+      // two accumulators (one per N tile of a unit) + four A stages share the 512 TMEM columns: N <= 192.
+      // An even number of N tiles covers Pp with the least overhang (weights beyond Pp: TMA zero fill).
+      Geom g0 = g;
+      int best = 1 << 30;
+      for (int t = 1; t <= Pp / 32; ++t) {
+        const int bn = ((Pp + 2 * t - 1) / (2 * t) + 31) / 32 * 32;
+        if (bn > PAIR_BN_MAX) continue;
+        if (2 * t * bn < best) { best = 2 * t * bn; g0.BN = bn; g0.tiles_n = 2 * t; }
+      }
       p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
       memset(&p.mapA, 0, sizeof(p.mapA));

@@ -23,6 +23,10 @@ constexpr int SYNTH_WARPS = 8;
 template <class P>
 constexpr int block_threads() { return 64 + 32 * P::kEpiWarps + (P::kSynthA ? 32 * SYNTH_WARPS : 0); }
 constexpr int SMEM_LIMIT = 227 * 1024;
+// kBPair: two N tiles (<= 192 wide each) share every A stage; the B stage holds both
+constexpr int PAIR_BN_MAX = 192;
+template <class P>
+__host__ __device__ constexpr int b_stage_bytes() { return P::kBPair ? 2 * PAIR_BN_MAX * BK * 2 : B_STAGE_BYTES_MAX; }
 
 struct Ctl {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2];
@@ -34,7 +38,7 @@ constexpr int CTL_BYTES = (sizeof(Ctl) + 63) & ~63;
 // dynamic shared memory of a policy: 1 KB alignment slack + stages + control block + policy scratch
 template <class P>
 constexpr size_t smem_bytes() {
-  return 1024 + (size_t)P::kStages * ((P::kATmem ? 0 : P::kATiles * A_STAGE_BYTES) + B_STAGE_BYTES_MAX) + CTL_BYTES + P::kExtraBytes;
+  return 1024 + (size_t)P::kStages * ((P::kATmem ? 0 : P::kATiles * A_STAGE_BYTES) + b_stage_bytes<P>()) + CTL_BYTES + P::kExtraBytes;
 }
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int cols) {
@@ -67,6 +71,9 @@ struct MNMajorB {
 //                        and the MMA reads it from there -- no shared-memory traffic for A; 32 columns per stage),
 //   static constexpr int kATiles (128-row A tiles that share one B stage: accumulators side by side in TMEM),
 //                        kAccBufs (1 or 2 accumulator buffers; kAccBufs * kATiles * bn() <= 512 columns)
+//   static constexpr bool kBPair (needs kAccBufs == 2, kEpiWarps == 8): a unit covers N tiles 2*n_tile and
+//                        2*n_tile+1; both are multiplied with the same A stage (the two accumulator buffers hold the
+//                        two tiles, each drained by its own four epilogue warps) -- halves the A work per flop
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
 //   int k_chunks(Unit) const (>= 1); int bn() const  (UMMA N of this launch)
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
@@ -87,7 +94,8 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   constexpr int A_BYTES = P::kATmem ? 0 : P::kATiles * A_STAGE_BYTES;
   constexpr int A_TMEM_COLS = BK / 2;        // one stage of A in tensor memory: 64 bf16 per row = 32 columns
   uint8_t* sB = sA + STAGES * A_BYTES;
-  Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_STAGE_BYTES_MAX);
+  constexpr int B_BYTES = b_stage_bytes<P>();
+  Ctl* ctl = reinterpret_cast<Ctl*>(sB + STAGES * B_BYTES);
   uint8_t* extra = reinterpret_cast<uint8_t*>(ctl) + CTL_BYTES;
   uint8_t* extra_synth = extra + P::kExtraBytes / 2;
 
@@ -101,8 +109,8 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
 
   if (warp == 0 && lane == 0) prm.prefetch();
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? SYNTH_WARPS : 0)); mbar_init(&ctl->empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], P::kEpiWarps); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1 + (P::kSynthA ? (P::kSynthAlternate ? SYNTH_WARPS / 2 : SYNTH_WARPS) : 0)); mbar_init(&ctl->empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->tfull[b], 1); mbar_init(&ctl->tempty[b], P::kBPair ? 4 : P::kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&ctl->tmem_base, ncols);
@@ -122,7 +130,12 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
           if constexpr (!P::kSynthA) prm.load_a(sA + stage * A_BYTES, &ctl->full[stage], un, kc);
-          prm.load_b(sB + stage * B_STAGE_BYTES_MAX, &ctl->full[stage], un, kc);
+          if constexpr (P::kBPair) {
+            prm.load_b(sB + stage * B_BYTES, &ctl->full[stage], Unit{un.m_tile, 2 * un.n_tile, un.z}, kc);
+            prm.load_b(sB + stage * B_BYTES + BN * BK * 2, &ctl->full[stage], Unit{un.m_tile, 2 * un.n_tile + 1, un.z}, kc);
+          } else {
+            prm.load_b(sB + stage * B_BYTES, &ctl->full[stage], un, kc);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -134,6 +147,28 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
       int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
       for (int it = 0; it < n_iters; ++it) {
         const int KC = prm.k_chunks(prm.unit((int)blockIdx.x, (int)gridDim.x, it));
+        if constexpr (P::kBPair) {
+          static_assert(!P::kBPair || (P::kATmem && P::kAccBufs == 2 && P::kEpiWarps == 8 && P::kATiles == 1), "kBPair layout");
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+            const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              if (kc == 0) { mbar_wait(&ctl->tempty[sub], bphase ^ 1); tc_fence_after(); }
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16_ts(tmem_base + (uint32_t)(sub * BN), a_tmem + (uint32_t)(k * (UMMA_K / 2)),
+                             prm.b_desc(b_addr + (uint32_t)(sub * BN * BK * 2), k), idesc, (kc | k) != 0);
+              if (kc == KC - 1) umma_commit(&ctl->tfull[sub]);
+            }
+            umma_commit(&ctl->empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          bphase ^= 1;
+          continue;
+        }
         mbar_wait(&ctl->tempty[buf], bphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
@@ -141,7 +176,7 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES_MAX);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
           if constexpr (P::kATmem) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
 #pragma unroll
@@ -169,6 +204,33 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
     const int sub = (warp - 2) >> 2;        // kEpiWarps == 8: which of the two warps of this quarter
     typename P::Epilogue epi(prm, extra, row, warp - 2);
     int buf = 0; uint32_t bphase = 0;
+    if constexpr (P::kBPair) {
+      // warps of group `sub` own accumulator `sub` = N tile 2*n_tile + sub of every unit
+      for (int it = 0; it < n_iters; ++it) {
+        const Unit un0 = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
+        const Unit un = {un0.m_tile, 2 * un0.n_tile + sub, un0.z};
+        mbar_wait(&ctl->tfull[sub], bphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(sub * BN) + ((uint32_t)(q * 32) << 16);
+        epi.begin(un);
+        // the drain is not hidden behind the next unit's MMAs here: keep the next chunk's TMEM load in flight
+        float v[2][32];
+        tmem_ld32(taddr, v[0]);
+#pragma unroll
+        for (int c = 0; c < PAIR_BN_MAX / 32; ++c) {
+          if (c * 32 < BN) {
+            tmem_ld_wait();
+            if ((c + 1) * 32 < BN) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+            epi.chunk(un, c * 32, v[c & 1]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tempty[sub]);
+        epi.end(un);
+        bphase ^= 1;
+      }
+    } else
     for (int it = 0; it < n_iters; ++it) {
       const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
       mbar_wait(&ctl->tfull[buf], bphase);
@@ -192,29 +254,41 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   } else {
     // ------------------------------------------------------------------ A synthesis (kSynthA only)
     if constexpr (P::kSynthA) {
-      // 256 producer threads: row = TMEM lane quarter of this warp * 32 + lane, half = which group of four warps
-      const int t = (((warp - 2 - P::kEpiWarps) >> 2) << 7) + (warp & 3) * 32 + lane;
+      // 256 producer threads: row = TMEM lane quarter of this warp * 32 + lane; grp = which group of four warps.
+      // Normal mode: both groups build one stage together (grp = which half of the 64-wide row).
+      // kSynthAlternate: the groups take alternate stages (a thread builds its whole row), so the latency
+      // chain of one stage (LDS -> math -> st -> wait) overlaps with the other group's stage.
+      const int grp = (warp - 2 - P::kEpiWarps) >> 2;
+      const int row = (warp & 3) * 32 + lane;
+      const int t = (grp << 7) + row;
       typename P::SynthState sst;            // per-thread producer state that lives across stages
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0; int seq = 0;
       for (int it = 0; it < n_iters; ++it) {
         const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
         const int KC = prm.k_chunks(un);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         prm.synth_begin(un, extra_synth, t, sst);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(&ctl->empty[stage], phase ^ 1);
-          if constexpr (P::kATmem) {
-            const uint32_t ta = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS) + ((uint32_t)((warp & 3) * 32) << 16);
-            prm.synth_a_tmem(ta, un, kc, t, extra_synth, sst);
-            tmem_st_wait();
-            tc_fence_before();
-          } else {
-            prm.synth_a(sA + stage * A_BYTES, un, kc, t, extra_synth, sst);
-            fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core
+        for (int kc = 0; kc < KC; ++kc, ++seq) {
+          if (!P::kSynthAlternate || (seq & 1) == grp) {
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            if constexpr (P::kATmem) {
+              const uint32_t ta = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS) + ((uint32_t)((warp & 3) * 32) << 16);
+              if constexpr (P::kSynthAlternate) {
+                prm.synth_a_tmem(ta, un, kc, row, extra_synth, sst);
+                prm.synth_a_tmem(ta, un, kc, 128 + row, extra_synth, sst);
+              } else {
+                prm.synth_a_tmem(ta, un, kc, t, extra_synth, sst);
+              }
+              tmem_st_wait();
+              tc_fence_before();
+            } else {
+              prm.synth_a(sA + stage * A_BYTES, un, kc, t, extra_synth, sst);
+              fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->full[stage]);
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
