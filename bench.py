@@ -136,6 +136,22 @@ def algorithmic_work(spec, tag, B, world):
     return "bytes", 0.0
 
 
+def ncu_traffic(spec, tag, B, precision):
+    """DRAM bytes of one launch of `tag` from the committed ncu --set full capture (profiles/), or None when
+    the capture was taken on another workload."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return None
+    w = t.get("workload", {})
+    if (w.get("name"), w.get("F"), w.get("K"), w.get("B"), w.get("precision")) != (spec["name"], spec["F"], spec["K"], B, precision):
+        return None
+    k = t.get("kernels", {}).get(tag)
+    return k["traffic_bytes"] if k else None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,19 +269,20 @@ def run_ours(args):
                 kernel_table[tag]["achieved"] = round(rate / (1e12 if kind == "flops" else 1e9), 3)
                 kernel_table[tag]["unit"] = "TFLOP/s" if kind == "flops" else "GB/s"
         top = next(iter(kernel_table))
+        traffic = ncu_traffic(spec, top, B, args.precision)
         kind, amount = algorithmic_work(spec, top, B, world)
         avg_ms = kernel_table[top]["avg_ms"]
         if kind == "flops" and amount > 0:
             ach = amount / (avg_ms / 1e3) / 1e12
             peak = pk["tflops_sustained"]
             roof = {"kernel": top, "bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(ach / peak, 5), "traffic": None, "share_of_step": kernel_table[top]["share"],
+                    "frac": round(ach / peak, 5), "traffic": traffic, "share_of_step": kernel_table[top]["share"],
                     "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
                     "algorithmic_flops_per_launch": amount}
         else:
             ach = (amount / (avg_ms / 1e3) / 1e9) if amount else 0.0
             roof = {"kernel": top, "bound": "hbm", "achieved": round(ach, 3), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(ach / pk["hbm_gbs"], 5), "traffic": None, "share_of_step": kernel_table[top]["share"],
+                    "frac": round(ach / pk["hbm_gbs"], 5), "traffic": traffic, "share_of_step": kernel_table[top]["share"],
                     "peak_source": pk["source"], "algorithmic_bytes_per_launch": amount}
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only ----

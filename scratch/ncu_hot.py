@@ -4,7 +4,7 @@ import csv, subprocess, sys, io, collections
 rep = sys.argv[1]; kre = sys.argv[2] if len(sys.argv) > 2 else None; top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr, units, data = rows[0], rows[1], rows[2:]
-want = ['Kernel Name', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active_realtime.avg.pct', 'dram__bytes_read.sum ', 'dram__bytes_write.sum ',
+want = ['Kernel Name', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum ', 'dram__bytes_write.sum ',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct', 'lts__t_sectors.avg.pct', 'sm__cycles_elapsed.avg.per_second',
         'smsp__issue_active.avg.pct', 'launch__registers_per_thread ', 'sm__inst_executed.sum ', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum ']
 for i, h in enumerate(hdr):
