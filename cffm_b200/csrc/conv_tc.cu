@@ -56,20 +56,31 @@ struct ConvFwdTC : KMajorA, KMajorB {
   // layer 0: the synthesised cube slab goes to tensor memory (tcgen05.st) and the MMA reads A from there:
   // the kernel was bound by shared-memory bandwidth (STS of the slab + UMMA reads of A and B + LDS of the rows)
   // ... and every slab feeds two N tiles (kBPair): the producers, not the tensor pipe, bounded the kernel
-  static constexpr bool kATmem = L0, kSynthAlternate = L0, kBPair = L0;
+  static constexpr bool kATmem = L0, kSynthAlternate = L0, kBPair = L0, kEpiPrefetch = false;
   CUtensorMap mapA, mapB;
   Geom g;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
+  float* pool_part;         // l >= 1, tiles_n > 1: pooled sums per N tile [tiles_n][B*Ho], added up by k_pool_parts
   const float* rows; const int* pair_i; const int* pair_j;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
   __device__ int bn() const { return g.BN; }
   __device__ int m_tiles() const { return (g.M + BM - 1) / BM; }
+  // Layer 0 (A synthesised on chip): a CTA walks all units of its M tile.  Layers >= 1 read A (the im2col view
+  // of X_l) from memory once per N tile: neighbouring CTAs take the N tiles of ONE M tile at the same time, so
+  // the tile comes from DRAM once and from L2 for the others (a CTA walking its own M tile alone re-read it
+  // from DRAM: 148 tiles of 4*Pp*256 B do not fit L2).
   __device__ int n_iters(int cta, int ncta) const {
     const int mt = m_tiles();
-    return (cta < mt ? (mt - cta + ncta - 1) / ncta : 0) * units_n();
+    if (L0) return (cta < mt ? (mt - cta + ncta - 1) / ncta : 0) * units_n();
+    const int n = mt * g.tiles_n;
+    return cta < n ? (n - cta + ncta - 1) / ncta : 0;
   }
   __device__ int units_n() const { return L0 ? g.tiles_n >> 1 : g.tiles_n; }   // layer 0: a unit = two N tiles
-  __device__ Unit unit(int cta, int ncta, int it) const { return {cta + (it / units_n()) * ncta, it % units_n(), 0}; }
+  __device__ Unit unit(int cta, int ncta, int it) const {
+    if (L0) return {cta + (it / units_n()) * ncta, it % units_n(), 0};
+    const int u = cta + it * ncta;
+    return {u / g.tiles_n, u % g.tiles_n, 0};
+  }
   __device__ int k_chunks(Unit) const { return 4 * g.Pp / BK; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(L0 ? 2 * g.BN * BK * 2 : A_STAGE_BYTES + g.BN * BK * 2); }
   __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
@@ -147,7 +158,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
         asm volatile("bar.sync 2, 256;" ::: "memory");
       }
     }
-    __device__ void begin(Unit un) { if (un.n_tile < (L0 ? 2 : 1)) rowsum = 0.f; }
+    __device__ void begin(Unit un) { if (!L0 || un.n_tile < 2) rowsum = 0.f; }
     __device__ void chunk(Unit un, int c0, const float (&v)[32]) {
       const int m = un.m_tile * BM + row;
       const int n0 = un.n_tile * p.g.BN + c0;
@@ -179,7 +190,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
       }
     }
     __device__ void end(Unit un) {
-      if (un.n_tile < p.g.tiles_n - (L0 ? 2 : 1)) return;
+      if (L0 && un.n_tile < p.g.tiles_n - 2) return;
       const int m = un.m_tile * BM + row;
       float s = m < p.g.M ? rowsum : 0.f;
       for (int off = p.g.Ho >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -192,11 +203,23 @@ struct ConvFwdTC : KMajorA, KMajorB {
         s += *slot;
       }
       int b, h, w; p.g.pos(m, b, h, w);
-      if (w == 0 && m < p.g.M) p.t1[(int64_t)b * p.t1_dim + p.sp_off + h] = s;
+      if (w == 0 && m < p.g.M) {
+        if (L0 || p.g.tiles_n == 1) p.t1[(int64_t)b * p.t1_dim + p.sp_off + h] = s;
+        else p.pool_part[(int64_t)un.n_tile * p.g.B * p.g.Ho + (int64_t)b * p.g.Ho + h] = s;
+      }
     }
     __device__ void finish() {}
   };
 };
+
+// t1[b, sp_off + h] = sum over N tiles (fixed order) of the pooled partial sums of forward layers >= 1
+__global__ void k_pool_parts(const float* __restrict__ part, int tiles_n, int B, int Ho, float* __restrict__ t1, int t1_dim, int sp_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ho) return;
+  float s = 0.f;
+  for (int n = 0; n < tiles_n; ++n) s += part[(int64_t)n * B * Ho + i];
+  t1[(int64_t)(i / Ho) * t1_dim + sp_off + i % Ho] = s;
+}
 
 // =================================================================================================
 // Data gradient, layer l >= 1:
@@ -206,10 +229,9 @@ struct ConvFwdTC : KMajorA, KMajorB {
 template <int ACT>
 struct ConvDgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
-  // the reduction is short (Pp/64 stages per tile) and the epilogue waits on global loads of the mask:
-  // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks) keep up with the MMA
-  static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
-  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
+  // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks); scratch = their staging tiles
+  static constexpr int kStages = 4, kExtraBytes = 8 * 32 * 80, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = true;
   CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
@@ -227,35 +249,63 @@ struct ConvDgradTC : KMajorA, KMajorB {
   __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
   __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
   struct Epilogue {
-    const ConvDgradTC& p; int row; int64_t base; float dsp; bool ok;
-    __device__ Epilogue(const ConvDgradTC& p_, uint8_t*, int row_, int) : p(p_), row(row_), base(0), dsp(0.f), ok(false) {}
-    __device__ void begin(Unit un) {
-      const int m = un.m_tile * BM + row;
-      ok = m < p.g.M;
-      int b, h, w; p.g.pos(ok ? m : 0, b, h, w);
+    // K is short here (Pp/64 stages per unit), so the drain decides the speed, and a lane that loads and
+    // stores 64 B of its own row costs one L1 wavefront per lane.  Instead: the mask of the whole unit
+    // (this warp's four chunks) is requested -- before the accumulator is complete -- in a coalesced
+    // layout (4 lanes per row piece), the packed result goes through a per-warp staging tile in shared
+    // memory into the same layout, is masked there with bit operations and stored 8 rows per instruction.
+    static constexpr int STG = 80;   // staging row stride (64 B + 16: conflict-free 16-byte stores)
+    const ConvDgradTC& p; int row, sub, lane; float dsp;
+    uint8_t* stg;
+    int64_t cbase[4]; bool cok[4];   // rows (lane>>2) + 8i of this warp's 32: element offset of this lane's 8 channels
+    uint4 mk[MAX_BN / 64][4];
+    __device__ Epilogue(const ConvDgradTC& p_, uint8_t* ex, int row_, int ew)
+        : p(p_), row(row_), sub(ew >> 2), lane(threadIdx.x & 31), dsp(0.f), stg(ex + ew * 32 * STG) {}
+    __device__ void begin(Unit) {}
+    __device__ void prefetch(Unit un) {
       const int n0 = un.n_tile * p.g.BN;
       const int tap = n0 / p.g.Pp, pb = n0 - tap * p.g.Pp;
       const int dh = tap >> 1, dw = tap & 1;
-      base = (((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw) * p.g.Pp + pb;
-      dsp = ok ? __ldg(p.gout + b) * __ldg(p.v_head + p.sp_off + 2 * h + dh) : 0.f;
-    }
-    __device__ void chunk(Unit, int c0, const float (&v)[32]) {
-      if (!ok) return;
-      const uint4* xs = reinterpret_cast<const uint4*>(p.X + base + c0);
-      uint4* dst = reinterpret_cast<uint4*>(p.dYprev + base + c0);
+      {
+        const int m = un.m_tile * BM + row;
+        int b, h, w; p.g.pos(m < p.g.M ? m : 0, b, h, w);
+        dsp = m < p.g.M ? __ldg(p.gout + b) * __ldg(p.v_head + p.sp_off + 2 * h + dh) : 0.f;
+      }
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const uint4 xv = __ldg(xs + q4);
-        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-        uint32_t o[4];
+      for (int i = 0; i < 4; ++i) {
+        const int m = un.m_tile * BM + (row & ~31) + (lane >> 2) + 8 * i;
+        cok[i] = m < p.g.M;
+        int b, h, w; p.g.pos(cok[i] ? m : 0, b, h, w);
+        cbase[i] = (((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw) * p.g.Pp + pb + (lane & 3) * 8;
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = q4 * 8 + e * 2;
-          const float m0 = (xw[e] & 0x7FFFu) ? phi_scale<ACT>() : 0.f;        // X > 0  <=>  Y > 0
-          const float m1 = (xw[e] & 0x7FFF0000u) ? phi_scale<ACT>() : 0.f;
-          o[e] = pack2((v[j] + dsp) * m0, (v[j + 1] + dsp) * m1);
+      for (int ci = 0; ci < MAX_BN / 64; ++ci) {
+        const int c0 = (2 * ci + sub) * 32;
+        if (c0 < p.g.BN) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            mk[ci][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + cbase[i] + c0)) : make_uint4(0u, 0u, 0u, 0u);
         }
-        dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    static __device__ __forceinline__ uint32_t keep_bits(uint32_t x) {   // X > 0  <=>  Y > 0, per bf16 half
+      return ((x & 0x7FFFu) ? 0xFFFFu : 0u) | ((x & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
+    }
+    __device__ __forceinline__ void chunk_i(Unit, int ci, int c0, const float (&v)[32]) {
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) o[j >> 1] = pack2((v[j] + dsp) * phi_scale<ACT>(), (v[j + 1] + dsp) * phi_scale<ACT>());
+      __syncwarp();                                   // the previous chunk has been read out of the staging tile
+      uint4* mine = reinterpret_cast<uint4*>(stg + lane * STG);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mine[q4] = make_uint4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 d = *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * STG + (lane & 3) * 16);
+        const uint4 x = mk[ci][i];
+        d.x &= keep_bits(x.x); d.y &= keep_bits(x.y); d.z &= keep_bits(x.z); d.w &= keep_bits(x.w);
+        if (cok[i]) *reinterpret_cast<uint4*>(p.dYprev + cbase[i] + c0) = d;
       }
     }
     __device__ void end(Unit) {}
@@ -274,7 +324,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   static constexpr int kStages = 3, kExtraBytes = 72 * 1024, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
-  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
   CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
   Geom g;                   // Ho = 16: 256 rows per sample
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
@@ -462,7 +512,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
   // their accumulators sit side by side in TMEM (2 x 256 columns, one buffer: the units are long)
   static constexpr int kATiles = L0 ? 2 : 1, kAccBufs = L0 ? 1 : 2, kEpiWarps = 4;
-  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
   static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
   static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
   CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
@@ -679,6 +729,7 @@ struct TCState {
   float* wg_partial = nullptr;   // weight-gradient split scratch
   int64_t wg_partial_floats = 0;
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
+  float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
   TmaEncoder enc;
 };
 
@@ -717,6 +768,7 @@ int tc_alloc(Model* m, bool train) {
     const int64_t B = m->max_batch, Pp = st->Pp;
     for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
     for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
+    TCTRY(tcmalloc(m, &st->pool_part, (Pp / st->BN) * B * (m->Ko >> 2)));
   }
   if (train && !st->dY[0]) {
     const int64_t B = m->max_batch, Pp = st->Pp;
@@ -738,6 +790,7 @@ void tc_free(Model* m) {
   for (int l = 0; l < kMaxConv; ++l) { if (st->dY[l]) cudaFree(st->dY[l]); if (st->Wt[l]) cudaFree(st->Wt[l]); if (st->Wd[l]) cudaFree(st->Wd[l]); }
   if (st->wg_partial) cudaFree(st->wg_partial);
   if (st->bg_partial) cudaFree(st->bg_partial);
+  if (st->pool_part) cudaFree(st->pool_part);
   delete st;
   m->tcs = nullptr;
 }
@@ -819,17 +872,21 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
         if (2 * t * bn < best) { best = 2 * t * bn; g0.BN = bn; g0.tiles_n = 2 * t; }
       }
       p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
-      p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
+      p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j; p.pool_part = nullptr;
       memset(&p.mapA, 0, sizeof(p.mapA));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g0.BN, 64));
       TCTRY(launch_tc(m, p, m_tiles, s));
     } else {
       ConvFwdTC<ACT, false> p;
       p.g = g; p.bias = m->dense_w + m->lay.conv_b[l]; p.Xout = st->X[l + 1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
-      p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr;
+      p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr; p.pool_part = st->pool_part;
       TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[l], Pp, 4 * Pp, g.BN, 64));
-      TCTRY(launch_tc(m, p, m_tiles, s));
+      TCTRY(launch_tc(m, p, m_tiles * g.tiles_n, s));
+      if (g.tiles_n > 1) {
+        k_pool_parts<<<(B * g.Ho + 255) / 256, 256, 0, s>>>(st->pool_part, g.tiles_n, B, g.Ho, m->t1, m->t1_dim, off);
+        m->launches++;
+      }
     }
     off += g.Ho;
   }

@@ -40,7 +40,7 @@ struct PlainGemm : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN); }
   static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
-  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
   CUtensorMap mapA, mapB;   // A: dims (K, M) box (64, 128); B: dims (K, N) box (64, BN)
   float* C; int M, N, K, BN, tiles_n;
   __device__ int bn() const { return BN; }
@@ -76,7 +76,7 @@ struct PlainGemm : KMajorA, KMajorB {
 struct PlainGemmTN : MNMajorA, MNMajorB {
   static constexpr bool kSynthA = false;
   static constexpr int kStages = 4, kExtraBytes = 0, kATiles = 1, kAccBufs = 2, kEpiWarps = 4;
-  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false;
+  static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
   CUtensorMap mapA, mapB;   // A: dims (M, R) box (64, 64); B: dims (N, R) box (64, 64)
   float* C; int M, N, R, BN, tiles_n;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, BN, true, true); }

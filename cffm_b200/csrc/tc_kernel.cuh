@@ -74,6 +74,8 @@ struct MNMajorB {
 //   static constexpr bool kBPair (needs kAccBufs == 2, kEpiWarps == 8): a unit covers N tiles 2*n_tile and
 //                        2*n_tile+1; both are multiplied with the same A stage (the two accumulator buffers hold the
 //                        two tiles, each drained by its own four epilogue warps) -- halves the A work per flop
+//   static constexpr bool kEpiPrefetch: the epilogue object has prefetch(Unit) (called before the accumulator is
+//                        complete) and chunk_i(Unit, ci, c0, v) for its ci-th chunk instead of chunk()
 //   int n_iters(cta, ncta) const; Unit unit(cta, ncta, it) const  -- the unit sequence of one CTA
 //   int k_chunks(Unit) const (>= 1); int bn() const  (UMMA N of this launch)
 //   void load_a(uint8_t* sA, uint64_t* bar, Unit, int kc) const      -- TMA for the A stage (!kSynthA)
@@ -229,6 +231,35 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
         if (lane == 0) mbar_arrive(&ctl->tempty[sub]);
         epi.end(un);
         bphase ^= 1;
+      }
+    } else if constexpr (P::kEpiPrefetch) {
+      // eight warps, chunk (2*ci + sub) of the accumulator belongs to warp group `sub`: the policy issues its
+      // global loads for the whole unit before the accumulator is complete (they overlap the unit's MMAs),
+      // and the TMEM load of the next chunk stays in flight behind the current one
+      static_assert(!P::kEpiPrefetch || (P::kEpiWarps == 8 && P::kATiles == 1), "kEpiPrefetch layout");
+      for (int it = 0; it < n_iters; ++it) {
+        const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
+        epi.prefetch(un);
+        mbar_wait(&ctl->tfull[buf], bphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(buf * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+        epi.begin(un);
+        float v[2][32];
+        if (sub * 32 < ACC_COLS) tmem_ld32(taddr + (uint32_t)(sub * 32), v[0]);
+#pragma unroll
+        for (int ci = 0; ci < MAX_BN / 64; ++ci) {
+          const int c0 = (2 * ci + sub) * 32;
+          if (c0 < ACC_COLS) {
+            tmem_ld_wait();
+            if (c0 + 64 < ACC_COLS) tmem_ld32(taddr + (uint32_t)(c0 + 64), v[(ci + 1) & 1]);
+            epi.chunk_i(un, ci, c0, v[ci & 1]);   // ci is a constant after unrolling
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tempty[buf]);
+        epi.end(un);
+        if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
       }
     } else
     for (int it = 0; it < n_iters; ++it) {

@@ -14,6 +14,8 @@ SHAPES = {
     "mltag_like": (3, 200, 64, "elu"),         # P=3  -> 64 (mostly padding)
     "criteo_like": (39, 2000, 6, "relu"),      # P=741 -> 768 channels, three N tiles of 256
     "odd_batch": (12, 500, 7, "prelu"),        # P=66 -> 128, BN=128; partial M tiles everywhere
+    "overhang": (30, 900, 5, "relu"),          # P=435 -> 448: layer-0 forward covers it with 4 x 128 (64 columns of zero fill)
+    "three_by_64": (20, 700, 9, "elu"),        # P=190 -> 192: layer-0 forward pairs two N tiles of 96
 }
 
 
