@@ -1,0 +1,271 @@
+// Layer-0 forward in factorised form (included by conv_tc.cu).
+//
+// The interaction cube is rank one per pair (CFFM.py:355-367: X0[a,c,p] = o_i[a] o_j[c]), so the 2x2/s2
+// convolution over it (CFFM.py:420-438) is a bilinear form per output channel q:
+//
+//   Y0[b,h,w,q] = a_{b,h}^T  Wq  a_{b,w},     a_{b,h}[2i+dh] = o_i[b, 2h+dh]   (2F numbers)
+//                                             Wq[2i+dh, 2j+dw] = W0[dh,dw,(i,j),q] for i < j, else 0
+//
+//   step 1   Z[(b,h), n] = sum_k A[(b,h), k] Wq[k, n]          tcgen05 SS MMA, M=128 (8 samples x 16 h), N=K=KA
+//   step 2   D[(b,h), (b',w)] = sum_n Z[(b,h), n] A[(b',w), n]  tcgen05 TS MMA (Z as bf16 in TMEM), N=128, K=KA
+//            Y0[b,h,w,q] = D[(b,h), (b,w)]  (the 16 columns of the row's own sample)
+//
+// Step 1 is 2*KA^2 flops per (row, q) instead of 2*16*4P for the sixteen w of that row in the direct form
+// (7.5x fewer at F=39); step 2 wastes 7/8 of its columns (a tile holds 8 samples) and still costs less than
+// step 1.  The A tile (128 x KA bf16, K-major SWIZZLE_128B) is both the A operand of step 1 and the B operand
+// of step 2.
+//
+//   warp 0      TMA: one weight slab Wq^T (KA x KA, two 64-wide blocks when KA > 64) per q into a ring
+//   warp 1      MMA issuer: step 1 of q, then step 2 of q-2 (the conversion of q-1 overlaps both)
+//   warps 2..5  converters: Z fp32 (TMEM) -> bf16 -> TMEM (A operand of step 2)
+//   warps 6..9  epilogue: own 16 columns of D + bias, activation, pooling sums; 16 channels are collected in
+//               registers so that every store is a full 32-byte sector of X1[b,h,w,:]; they also build the A tile
+// (included inside namespace cffm::tc of conv_tc.cu, after pack2 / phi_f)
+#pragma once
+
+constexpr int F0_NST = 4;
+constexpr int F0_KA_MAX = 80;
+constexpr int F0_SLAB_BYTES = 2 * F0_KA_MAX * 128;
+constexpr int F0_THREADS = 320;
+constexpr int F0_D1 = 0, F0_D1_STRIDE = 80, F0_ZB = 160, F0_ZB_STRIDE = 48, F0_D2 = 256, F0_D2_STRIDE = 128;
+constexpr int F0_BIAS_MAX = 1280;
+
+struct F0Ctl {
+  uint64_t full_b[F0_NST], empty_b[F0_NST];
+  uint64_t d1_full[2], d1_empty[2], zb_full[2], zb_empty[2], d2_full[2], d2_empty[2];
+  uint64_t a_ready;
+  uint32_t tmem_base, pad;
+};
+constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4;
+static_assert(sizeof(F0Ctl) <= 256, "control block");
+
+struct Fwd0FactParams {
+  CUtensorMap mapW;     // Wf0 viewed as [Q16*KA rows][nblk*64 cols] bf16, box (64, KA)
+  const float* rows;    // outer rows [B][F][32]
+  const float* bias;
+  bf16* Xout;           // X1 [B][16][16][Pp]
+  float* t1; int t1_dim, sp_off;
+  int B, F, P, Pp, KA, nblk, Q16;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// Wf0[q][n = 2j+dw][k = 2i+dh] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
+__global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restrict__ pair_i, const int* __restrict__ pair_j, int P,
+                               int KA, int KP, bf16* __restrict__ out) {
+  const int64_t total = 4ll * P * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e % P);
+    const int64_t r = e / P;
+    const int p = (int)(r % P), tap = (int)(r / P);
+    const int dh = tap >> 1, dw = tap & 1;
+    const int k = 2 * pair_i[p] + dh, n = 2 * pair_j[p] + dw;
+    out[((int64_t)q * KA + n) * KP + k] = __float2bfloat16(W0[e]);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_constant__ Fwd0FactParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B]
+  uint8_t* sW = sAt + 2 * A_STAGE_BYTES;                 // ring of weight slabs
+  F0Ctl* ctl = reinterpret_cast<F0Ctl*>(sW + F0_NST * F0_SLAB_BYTES);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 256);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int KA = prm.KA, nblk = prm.nblk, Q = prm.Q16;
+  const int n_tiles = (prm.B + 7) >> 3;
+  const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t slab_bytes = (uint32_t)(nblk * KA * 128);
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&prm.mapW);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < F0_NST; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctl->d1_full[b], 1); mbar_init(&ctl->d1_empty[b], 4);
+      mbar_init(&ctl->zb_full[b], 4); mbar_init(&ctl->zb_empty[b], 1);
+      mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 4);
+    }
+    mbar_init(&ctl->a_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&ctl->tmem_base, 512);
+  for (int e = threadIdx.x; e < Q; e += F0_THREADS) sbias[e] = e < prm.P ? __ldg(prm.bias + e) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA: weight slabs
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t)
+        for (int q = 0; q < Q; ++q, ++n) {
+          const int s = n % F0_NST; const uint32_t ph = (n / F0_NST) & 1;
+          mbar_wait(&ctl->empty_b[s], ph ^ 1);
+          mbar_arrive_expect_tx(&ctl->full_b[s], slab_bytes);
+          for (int blk = 0; blk < nblk; ++blk)
+            tma_load_2d(sW + s * F0_SLAB_BYTES + blk * KA * 128, &prm.mapW, &ctl->full_b[s], blk * 64, q * KA);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(BM, KA), idesc2 = umma_idesc_bf16(BM, 128);
+      const uint32_t at_addr = smem_u32(sAt);
+      const int ksteps = KA / UMMA_K;
+      auto step2 = [&](uint32_t m) {
+        const int buf = m & 1; const uint32_t bph = (m >> 1) & 1;
+        mbar_wait(&ctl->zb_full[buf], bph);
+        mbar_wait(&ctl->d2_empty[buf], bph ^ 1);
+        tc_fence_after();
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ts(tmem_base + (uint32_t)(F0_D2 + buf * F0_D2_STRIDE), tmem_base + (uint32_t)(F0_ZB + buf * F0_ZB_STRIDE + k * 8),
+                       umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2), idesc2, k != 0);
+        umma_commit(&ctl->zb_empty[buf]);
+        umma_commit(&ctl->d2_full[buf]);
+      };
+      uint32_t n = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
+        tc_fence_after();
+        for (int q = 0; q < Q; ++q, ++n) {
+          const int s = n % F0_NST; const uint32_t ph = (n / F0_NST) & 1;
+          const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
+          mbar_wait(&ctl->full_b[s], ph);
+          mbar_wait(&ctl->d1_empty[buf], bph ^ 1);
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(sW + s * F0_SLAB_BYTES);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + (uint32_t)(F0_D1 + buf * F0_D1_STRIDE),
+                      umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2),
+                      umma_desc_k_sw128(w_addr + (uint32_t)((k >> 2) * KA * 128)) + (uint64_t)((k & 3) * 2), idesc1, k != 0);
+          umma_commit(&ctl->empty_b[s]);
+          umma_commit(&ctl->d1_full[buf]);
+          if (q >= 2) step2(n - 2);
+        }
+        if (Q >= 2) step2(n - 2);
+        step2(n - 1);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ converters: Z fp32 -> bf16 A operand
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t n = 0;
+    for (int t = 0; t < my_tiles; ++t)
+      for (int q = 0; q < Q; ++q, ++n) {
+        const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
+        mbar_wait(&ctl->d1_full[buf], bph);
+        tc_fence_after();
+        float v[F0_KA_MAX / 16][16];
+#pragma unroll
+        for (int c = 0; c < F0_KA_MAX / 16; ++c)
+          if (c * 16 < KA) tmem_ld16(tmem_base + lane_off + (uint32_t)(F0_D1 + buf * F0_D1_STRIDE + c * 16), v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->d1_empty[buf]);
+        mbar_wait(&ctl->zb_empty[buf], bph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < F0_KA_MAX / 16; ++c)
+          if (c * 16 < KA) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack2(v[c][2 * j], v[c][2 * j + 1]);
+            tmem_st8(tmem_base + lane_off + (uint32_t)(F0_ZB + buf * F0_ZB_STRIDE + c * 8), pk);
+          }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->zb_full[buf]);
+      }
+  } else {
+    // ------------------------------------------------------------------ epilogue (+ A tile builder)
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;                 // tile row: sample r>>4 of the tile, h = r&15
+    const int h = r & 15;
+    const bool hi = (lane & 16) != 0;             // second sample of this warp: columns 16..31 of the loaded 32
+    const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32);
+    auto build_a = [&](int tile) {
+      const int b = tile * 8 + (r >> 4);
+      const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
+      for (int c = 0; c < KA / 8; ++c) {          // 16-byte chunk c = fields 4c .. 4c+3
+        uint32_t wv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * c + e;
+          float2 o = make_float2(0.f, 0.f);
+          if (i < prm.F && b < prm.B) o = __ldg(reinterpret_cast<const float2*>(src + i * 32));
+          wv[e] = pack2(o.x, o.y);
+        }
+        *reinterpret_cast<uint4*>(sAt + (c >> 3) * A_STAGE_BYTES + sw128_offset(r, c & 7)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->a_ready);
+    };
+    if (my_tiles > 0) build_a((int)blockIdx.x);
+    uint32_t n = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b = tile * 8 + (r >> 4);
+      float rowsum = 0.f;
+      for (int q0 = 0; q0 < Q; q0 += 16) {
+        uint32_t acc[16][8];
+        float prev[16];
+#pragma unroll
+        for (int qq = 0; qq < 16; ++qq, ++n) {
+          const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
+          mbar_wait(&ctl->d2_full[buf], bph);
+          tc_fence_after();
+          float v[32];
+          tmem_ld32(d2_addr + (uint32_t)(buf * F0_D2_STRIDE), v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->d2_empty[buf]);
+          const float bq = sbias[q0 + qq];
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {
+            const float x = phi_f<ACT>((hi ? v[16 + w] : v[w]) + bq);
+            rowsum += x;
+            if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
+          }
+        }
+        if (b < prm.B) {
+          bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16) * prm.Pp + q0;
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {
+            uint4* d = reinterpret_cast<uint4*>(dst + (int64_t)w * prm.Pp);
+            d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+            d[1] = make_uint4(acc[w][4], acc[w][5], acc[w][6], acc[w][7]);
+          }
+        }
+      }
+      if (b < prm.B) prm.t1[(int64_t)b * prm.t1_dim + prm.sp_off + h] = rowsum;
+      // every MMA of this tile has retired (the last step-2 result was read above): the A tile may be rebuilt
+      if (t + 1 < my_tiles) build_a(tile + (int)gridDim.x);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}

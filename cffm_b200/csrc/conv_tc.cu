@@ -15,6 +15,8 @@
 // padded to a multiple of 64; master weights, optimizer state, pooling sums and all reductions
 // stay fp32.
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -713,6 +715,8 @@ __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restric
   dY[e] = __float2bfloat16_rn(gout[b] * v_lvl[h] * m);
 }
 
+#include "conv0_fact.cuh"
+
 }  // namespace tc
 
 // =================================================================================================
@@ -730,6 +734,8 @@ struct TCState {
   int64_t wg_partial_floats = 0;
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
   float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
+  bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
+  int KA = 0, nblk = 0, Q16 = 0;
   TmaEncoder enc;
 };
 
@@ -769,6 +775,15 @@ int tc_alloc(Model* m, bool train) {
     for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
     for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
     TCTRY(tcmalloc(m, &st->pool_part, (Pp / st->BN) * B * (m->Ko >> 2)));
+    const char* f0 = getenv("CFFM_FWD0");
+    if (2 * m->F <= F0_KA_MAX && !(f0 && !strcmp(f0, "direct"))) {   // factorised layer-0 forward
+      st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
+      const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
+      TCTRY(tcmalloc(m, &st->Wf0, n));
+      CFFM_CUDA_OK(m, cudaMemset(st->Wf0, 0, sizeof(bf16) * (size_t)n));
+      // channels Q16..Pp-1 of X1 are never written by that kernel
+      CFFM_CUDA_OK(m, cudaMemset(st->X[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
+    }
   }
   if (train && !st->dY[0]) {
     const int64_t B = m->max_batch, Pp = st->Pp;
@@ -791,6 +806,7 @@ void tc_free(Model* m) {
   if (st->wg_partial) cudaFree(st->wg_partial);
   if (st->bg_partial) cudaFree(st->bg_partial);
   if (st->pool_part) cudaFree(st->pool_part);
+  if (st->Wf0) cudaFree(st->Wf0);
   delete st;
   m->tcs = nullptr;
 }
@@ -837,6 +853,26 @@ static int launch_tc(Model* m, const Pol& p, int units_hint, cudaStream_t s) {
 }
 #define TC_MAP_OK(m, ok) do { if (!(ok)) { (m)->err = "cuTensorMapEncodeTiled failed"; return CFFM_ERR_CUDA; } } while (0)
 
+template <int ACT>
+static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream_t s) {
+  Fwd0FactParams p;
+  memset(&p.mapW, 0, sizeof(p.mapW));
+  TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1];
+  p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
+  p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_fwd0_fact<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F0_SMEM));
+    attr_done = true;
+  }
+  int grid = (B + 7) / 8; if (grid > 148) grid = 148;
+  k_fwd0_fact<ACT><<<grid, F0_THREADS, F0_SMEM, s>>>(p);
+  m->launches++;
+  CFFM_CUDA_OK(m, cudaGetLastError());
+  return CFFM_OK;
+}
+
 int tc_prep_weights(Model* m, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   CFFM_PROF(m, "prep_weights_bf16", s);
@@ -844,6 +880,10 @@ int tc_prep_weights(Model* m, cudaStream_t s) {
     const int64_t total = 4ll * st->Pp * st->Pp;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
     k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l]);
+    m->launches++;
+  }
+  if (st->Wf0) {
+    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0);
     m->launches++;
   }
   CFFM_CUDA_OK(m, cudaGetLastError());
@@ -860,7 +900,9 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     const std::string tag = "conv_fwd_l" + std::to_string(l);
     CFFM_PROF(m, tag.c_str(), s);
     const int m_tiles = (g.M + BM - 1) / BM;
-    if (l == 0) {
+    if (l == 0 && st->Wf0) {
+      TCTRY(fwd0_fact_launch<ACT>(m, st, B, off, s));
+    } else if (l == 0) {
       ConvFwdTC<ACT, true> p;
       // two accumulators (one per N tile of a unit) + four A stages share the 512 TMEM columns: N <= 192.
       // An even number of N tiles covers Pp with the least overhang (weights beyond Pp: TMA zero fill).
