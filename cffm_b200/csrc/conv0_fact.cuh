@@ -16,7 +16,7 @@
 // of step 2.
 //
 //   warp 0      TMA: one weight slab Wq^T (KA x KA, two 64-wide blocks when KA > 64) per q into a ring
-//   warp 1      MMA issuer: step 1 of q, then step 2 of q-2 (the conversion of q-1 overlaps both)
+//   warp 1      issues step 1, warp 10 issues step 2 (independent instruction streams, coupled by mbarriers only)
 //   warps 2..5  converters: Z fp32 (TMEM) -> bf16 -> TMEM (A operand of step 2)
 //   warps 6..9  epilogue: own 16 columns of D + bias, activation, pooling sums; 16 channels are collected in
 //               registers so that every store is a full 32-byte sector of X1[b,h,w,:]; they also build the A tile
@@ -26,7 +26,7 @@
 constexpr int F0_NST = 4;
 constexpr int F0_KA_MAX = 80;
 constexpr int F0_SLAB_BYTES = 2 * F0_KA_MAX * 128;
-constexpr int F0_THREADS = 320;
+constexpr int F0_THREADS = 352;
 constexpr int F0_D1 = 0, F0_D1_STRIDE = 80, F0_ZB = 160, F0_ZB_STRIDE = 48, F0_D2 = 256, F0_D2_STRIDE = 128;
 constexpr int F0_BIAS_MAX = 1280;
 
@@ -125,44 +125,65 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             tma_load_2d(sW + s * F0_SLAB_BYTES + blk * KA * 128, &prm.mapW, &ctl->full_b[s], blk * 64, q * KA);
         }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 step 1, warp 10 step 2
+    // One thread issuing both steps was the bottleneck (about 16 scalar instructions per tcgen05.mma): two
+    // independent streams, everything that does not depend on q hoisted, stage / buffer indices compile-time
+    // (F0_NST == 4 and Q % 4 == 0: slab stage = q & 3, TMEM buffer = q & 1, buffer phase = (q >> 1) & 1).
     if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_bf16(BM, KA), idesc2 = umma_idesc_bf16(BM, 128);
       const uint32_t at_addr = smem_u32(sAt);
       const int ksteps = KA / UMMA_K;
-      auto step2 = [&](uint32_t m) {
-        const int buf = m & 1; const uint32_t bph = (m >> 1) & 1;
-        mbar_wait(&ctl->zb_full[buf], bph);
-        mbar_wait(&ctl->d2_empty[buf], bph ^ 1);
-        tc_fence_after();
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(tmem_base + (uint32_t)(F0_D2 + buf * F0_D2_STRIDE), tmem_base + (uint32_t)(F0_ZB + buf * F0_ZB_STRIDE + k * 8),
-                       umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2), idesc2, k != 0);
-        umma_commit(&ctl->zb_empty[buf]);
-        umma_commit(&ctl->d2_full[buf]);
-      };
-      uint32_t n = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
-        tc_fence_after();
-        for (int q = 0; q < Q; ++q, ++n) {
-          const int s = n % F0_NST; const uint32_t ph = (n / F0_NST) & 1;
-          const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
-          mbar_wait(&ctl->full_b[s], ph);
-          mbar_wait(&ctl->d1_empty[buf], bph ^ 1);
+      uint64_t adesc[F0_KA_MAX / UMMA_K];
+#pragma unroll
+      for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+        adesc[k] = umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2);
+      if (warp == 1) {
+        const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
+        uint64_t wdesc[F0_NST], wk[F0_KA_MAX / UMMA_K];
+#pragma unroll
+        for (int s = 0; s < F0_NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * F0_SLAB_BYTES));
+#pragma unroll
+        for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
+        uint32_t it = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+          mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
           tc_fence_after();
-          const uint32_t w_addr = smem_u32(sW + s * F0_SLAB_BYTES);
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_base + (uint32_t)(F0_D1 + buf * F0_D1_STRIDE),
-                      umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2),
-                      umma_desc_k_sw128(w_addr + (uint32_t)((k >> 2) * KA * 128)) + (uint64_t)((k & 3) * 2), idesc1, k != 0);
-          umma_commit(&ctl->empty_b[s]);
-          umma_commit(&ctl->d1_full[buf]);
-          if (q >= 2) step2(n - 2);
+          for (int q = 0; q < Q; q += 4, ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              mbar_wait(&ctl->full_b[u], it & 1);
+              mbar_wait(&ctl->d1_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
+              tc_fence_after();
+              const uint32_t d1 = tmem_base + (uint32_t)(F0_D1 + (u & 1) * F0_D1_STRIDE);
+#pragma unroll
+              for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                if (k < ksteps) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
+              umma_commit(&ctl->empty_b[u]);
+              umma_commit(&ctl->d1_full[u & 1]);
+            }
+          }
         }
-        if (Q >= 2) step2(n - 2);
-        step2(n - 1);
+      } else {
+        const uint32_t idesc2 = umma_idesc_bf16(BM, 128);
+        for (int t = 0; t < my_tiles; ++t) {
+          mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
+          tc_fence_after();
+          for (int q = 0; q < Q; q += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              mbar_wait(&ctl->zb_full[u & 1], (uint32_t)(u >> 1));
+              mbar_wait(&ctl->d2_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
+              tc_fence_after();
+              const uint32_t d2 = tmem_base + (uint32_t)(F0_D2 + (u & 1) * F0_D2_STRIDE);
+              const uint32_t zb = tmem_base + (uint32_t)(F0_ZB + (u & 1) * F0_ZB_STRIDE);
+#pragma unroll
+              for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                if (k < ksteps) umma_bf16_ts(d2, zb + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
+              umma_commit(&ctl->zb_empty[u & 1]);
+              umma_commit(&ctl->d2_full[u & 1]);
+            }
+          }
+        }
       }
     }
   } else if (warp < 6) {
