@@ -16,17 +16,18 @@
 // of step 2.
 //
 //   warp 0      TMA: one weight slab Wq^T (KA x KA, two 64-wide blocks when KA > 64) per q into a ring
-//   warp 1      issues step 1, warp 10 issues step 2 (independent instruction streams, coupled by mbarriers only)
+//   warp 1      issues step 1, warp 14 issues step 2 (independent instruction streams, coupled by mbarriers only)
 //   warps 2..5  converters: Z fp32 (TMEM) -> bf16 -> TMEM (A operand of step 2)
-//   warps 6..9  epilogue: own 16 columns of D + bias, activation, pooling sums; 16 channels are collected in
-//               registers so that every store is a full 32-byte sector of X1[b,h,w,:]; they also build the A tile
+//   warps 6..13 epilogue: own columns of D (half of the sample's 16 each) + bias, activation, pooling sums; 16
+//               channels are collected in registers so that every store is a full 32-byte sector of X1[b,h,w,:];
+//               they also build the A tile
 // (included inside namespace cffm::tc of conv_tc.cu, after pack2 / phi_f)
 #pragma once
 
 constexpr int F0_NST = 4;
 constexpr int F0_KA_MAX = 80;
 constexpr int F0_SLAB_BYTES = 2 * F0_KA_MAX * 128;
-constexpr int F0_THREADS = 352;
+constexpr int F0_THREADS = 480;
 constexpr int F0_D1 = 0, F0_D1_STRIDE = 80, F0_ZB = 160, F0_ZB_STRIDE = 48, F0_D2 = 256, F0_D2_STRIDE = 128;
 constexpr int F0_BIAS_MAX = 1280;
 
@@ -36,7 +37,7 @@ struct F0Ctl {
   uint64_t a_ready;
   uint32_t tmem_base, pad;
 };
-constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4;
+constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4;
 static_assert(sizeof(F0Ctl) <= 256, "control block");
 
 struct Fwd0FactParams {
@@ -45,7 +46,7 @@ struct Fwd0FactParams {
   const float* bias;
   bf16* Xout;           // X1 [B][16][16][Pp]
   float* t1; int t1_dim, sp_off;
-  int B, F, P, Pp, KA, nblk, Q16;
+  int B, F, P, Pp, KA, nblk, Q16, split;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -57,6 +58,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
@@ -100,9 +108,9 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ctl->d1_full[b], 1); mbar_init(&ctl->d1_empty[b], 4);
       mbar_init(&ctl->zb_full[b], 4); mbar_init(&ctl->zb_empty[b], 1);
-      mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 4);
+      mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 8);
     }
-    mbar_init(&ctl->a_ready, 4);
+    mbar_init(&ctl->a_ready, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&ctl->tmem_base, 512);
@@ -125,12 +133,15 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             tma_load_2d(sW + s * F0_SLAB_BYTES + blk * KA * 128, &prm.mapW, &ctl->full_b[s], blk * 64, q * KA);
         }
     }
-  } else if (warp == 1 || warp == 10) {
-    // ------------------------------------------------------------------ MMA issuers: warp 1 step 1, warp 10 step 2
+  } else if (warp == 1 || warp == 14) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 step 1, warp 14 step 2
     // One thread issuing both steps was the bottleneck (about 16 scalar instructions per tcgen05.mma): two
     // independent streams, everything that does not depend on q hoisted, stage / buffer indices compile-time
     // (F0_NST == 4 and Q % 4 == 0: slab stage = q & 3, TMEM buffer = q & 1, buffer phase = (q >> 1) & 1).
-    if (lane == 0) {
+    {
+      // all lanes run the loop (uniform control flow); the MMAs and commits of one q sit inside ONE elect.sync
+      // region, which ptxas turns into straight-line UTCHMMA issue (a lane == 0 test costs a 16-instruction
+      // per-thread loop around every tcgen05 instruction)
       const uint32_t at_addr = smem_u32(sAt);
       const int ksteps = KA / UMMA_K;
       uint64_t adesc[F0_KA_MAX / UMMA_K];
@@ -139,6 +150,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
         adesc[k] = umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2);
       if (warp == 1) {
         const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
+        const int na = ((KA / 2) + 15) & ~15;   // split point (multiple of 16; rows of 128 B: 8-row groups stay whole)
+        const uint32_t idesc1a = umma_idesc_bf16(BM, na), idesc1b = umma_idesc_bf16(BM, KA - na);
         uint64_t wdesc[F0_NST], wk[F0_KA_MAX / UMMA_K];
 #pragma unroll
         for (int s = 0; s < F0_NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * F0_SLAB_BYTES));
@@ -154,17 +167,29 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
               mbar_wait(&ctl->full_b[u], it & 1);
               mbar_wait(&ctl->d1_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
               tc_fence_after();
+              if (elect_one()) {
               const uint32_t d1 = tmem_base + (uint32_t)(F0_D1 + (u & 1) * F0_D1_STRIDE);
+              if (prm.split) {   // two independent accumulation chains (columns 0..NA-1 and NA..KA-1), interleaved
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) {
+                    umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1a, k != 0);
+                    umma_bf16(d1 + (uint32_t)na, adesc[k], wdesc[u] + wk[k] + (uint64_t)(na * 8), idesc1b, k != 0);
+                  }
+              } else {
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
                 if (k < ksteps) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
+              }
               umma_commit(&ctl->empty_b[u]);
               umma_commit(&ctl->d1_full[u & 1]);
+              }
+              __syncwarp();
             }
           }
         }
       } else {
-        const uint32_t idesc2 = umma_idesc_bf16(BM, 128);
+        const uint32_t idesc2 = umma_idesc_bf16(BM, 128), idesc2h = umma_idesc_bf16(BM, 64);
         for (int t = 0; t < my_tiles; ++t) {
           mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
           tc_fence_after();
@@ -174,13 +199,25 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
               mbar_wait(&ctl->zb_full[u & 1], (uint32_t)(u >> 1));
               mbar_wait(&ctl->d2_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
               tc_fence_after();
+              if (elect_one()) {
               const uint32_t d2 = tmem_base + (uint32_t)(F0_D2 + (u & 1) * F0_D2_STRIDE);
               const uint32_t zb = tmem_base + (uint32_t)(F0_ZB + (u & 1) * F0_ZB_STRIDE);
+              if (prm.split) {
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) {
+                    umma_bf16_ts(d2, zb + (uint32_t)(k * 8), adesc[k], idesc2h, k != 0);
+                    umma_bf16_ts(d2 + 64u, zb + (uint32_t)(k * 8), adesc[k] + (uint64_t)(64 * 8), idesc2h, k != 0);
+                  }
+              } else {
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
                 if (k < ksteps) umma_bf16_ts(d2, zb + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
+              }
               umma_commit(&ctl->zb_empty[u & 1]);
               umma_commit(&ctl->d2_full[u & 1]);
+              }
+              __syncwarp();
             }
           }
         }
@@ -219,16 +256,20 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
         if (lane == 0) mbar_arrive(&ctl->zb_full[buf]);
       }
   } else {
-    // ------------------------------------------------------------------ epilogue (+ A tile builder)
+    // ------------------------------------------------------------------ epilogue (+ A tile builder), 8 warps
+    // Two warps per TMEM lane quarter: group 0 takes w = 0..7 of every channel, group 1 takes w = 8..15, so a
+    // thread keeps 8 x 16 results (64 registers) and still stores whole 32-byte sectors.
+    const int ew = warp - 6, grp = ew >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;                 // tile row: sample r>>4 of the tile, h = r&15
     const int h = r & 15;
-    const bool hi = (lane & 16) != 0;             // second sample of this warp: columns 16..31 of the loaded 32
-    const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32);
+    const bool hi = (lane & 16) != 0;             // second sample of this warp: its block starts 16 columns later
+    const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32 + grp * 8);
+    float* xch = sbias + F0_BIAS_MAX;             // pooling sums of group 1, [2][128]
     auto build_a = [&](int tile) {
       const int b = tile * 8 + (r >> 4);
       const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
-      for (int c = 0; c < KA / 8; ++c) {          // 16-byte chunk c = fields 4c .. 4c+3
+      for (int c = grp; c < KA / 8; c += 2) {     // 16-byte chunk c = fields 4c .. 4c+3
         uint32_t wv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -244,44 +285,47 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
       if (lane == 0) mbar_arrive(&ctl->a_ready);
     };
     if (my_tiles > 0) build_a((int)blockIdx.x);
-    uint32_t n = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile * 8 + (r >> 4);
       float rowsum = 0.f;
       for (int q0 = 0; q0 < Q; q0 += 16) {
-        uint32_t acc[16][8];
-        float prev[16];
+        uint32_t acc[8][8];
+        float prev[8];
 #pragma unroll
-        for (int qq = 0; qq < 16; ++qq, ++n) {
-          const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
-          mbar_wait(&ctl->d2_full[buf], bph);
+        for (int qq = 0; qq < 16; ++qq) {         // q & 1 == qq & 1, (q >> 1) & 1 == (qq >> 1) & 1
+          mbar_wait(&ctl->d2_full[qq & 1], (uint32_t)((qq >> 1) & 1));
           tc_fence_after();
-          float v[32];
-          tmem_ld32(d2_addr + (uint32_t)(buf * F0_D2_STRIDE), v);
+          float lo[8], up[8];
+          tmem_ld8(d2_addr + (uint32_t)((qq & 1) * F0_D2_STRIDE), lo);
+          tmem_ld8(d2_addr + (uint32_t)((qq & 1) * F0_D2_STRIDE + 16), up);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->d2_empty[buf]);
+          if (lane == 0) mbar_arrive(&ctl->d2_empty[qq & 1]);
           const float bq = sbias[q0 + qq];
 #pragma unroll
-          for (int w = 0; w < 16; ++w) {
-            const float x = phi_f<ACT>((hi ? v[16 + w] : v[w]) + bq);
+          for (int w = 0; w < 8; ++w) {
+            const float x = phi_f<ACT>((hi ? up[w] : lo[w]) + bq);
             rowsum += x;
             if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
           }
         }
         if (b < prm.B) {
-          bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16) * prm.Pp + q0;
+          bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
-          for (int w = 0; w < 16; ++w) {
+          for (int w = 0; w < 8; ++w) {
             uint4* d = reinterpret_cast<uint4*>(dst + (int64_t)w * prm.Pp);
             d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
             d[1] = make_uint4(acc[w][4], acc[w][5], acc[w][6], acc[w][7]);
           }
         }
       }
-      if (b < prm.B) prm.t1[(int64_t)b * prm.t1_dim + prm.sp_off + h] = rowsum;
+      // pooling sum of the row: the two groups meet in shared memory (double-buffered on the tile parity)
+      float* slot = xch + (t & 1) * BM + r;
+      if (grp == 1) *slot = rowsum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (grp == 0 && b < prm.B) prm.t1[(int64_t)b * prm.t1_dim + prm.sp_off + h] = rowsum + *slot;
       // every MMA of this tile has retired (the last step-2 result was read above): the A tile may be rebuilt
       if (t + 1 < my_tiles) build_a(tile + (int)gridDim.x);
     }
