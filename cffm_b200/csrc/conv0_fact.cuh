@@ -17,7 +17,8 @@
 //
 //   warp 0      TMA: one weight slab Wq^T (KA x KA, two 64-wide blocks when KA > 64) per q into a ring
 //   warp 1      issues step 1, warp 14 issues step 2 (independent instruction streams, coupled by mbarriers only)
-//   warps 2..5  converters: Z fp32 (TMEM) -> bf16 -> TMEM (A operand of step 2)
+//   warps 2..5  converters: Z fp32 (TMEM) -> bf16, written over the same TMEM columns (A operand of step 2);
+//               three Z buffers cover the latency of the step 1 -> convert -> step 2 ring
 //   warps 6..13 epilogue: own columns of D (half of the sample's 16 each) + bias, activation, pooling sums; 16
 //               channels are collected in registers so that every store is a full 32-byte sector of X1[b,h,w,:];
 //               they also build the A tile
@@ -28,12 +29,13 @@ constexpr int F0_NST = 4;
 constexpr int F0_KA_MAX = 80;
 constexpr int F0_SLAB_BYTES = 2 * F0_KA_MAX * 128;
 constexpr int F0_THREADS = 480;
-constexpr int F0_D1 = 0, F0_D1_STRIDE = 80, F0_ZB = 160, F0_ZB_STRIDE = 48, F0_D2 = 256, F0_D2_STRIDE = 128;
+constexpr int F0_NZ = 3;                  // Z buffers (step-1 accumulator, overwritten in place by its bf16 copy)
+constexpr int F0_Z = 0, F0_Z_STRIDE = 80, F0_D2 = 256, F0_D2_STRIDE = 128;
 constexpr int F0_BIAS_MAX = 1280;
 
 struct F0Ctl {
   uint64_t full_b[F0_NST], empty_b[F0_NST];
-  uint64_t d1_full[2], d1_empty[2], zb_full[2], zb_empty[2], d2_full[2], d2_empty[2];
+  uint64_t z_full[F0_NZ], z_empty[F0_NZ], zb_full[F0_NZ], d2_full[2], d2_empty[2];
   uint64_t a_ready;
   uint32_t tmem_base, pad;
 };
@@ -46,7 +48,7 @@ struct Fwd0FactParams {
   const float* bias;
   bf16* Xout;           // X1 [B][16][16][Pp]
   float* t1; int t1_dim, sp_off;
-  int B, F, P, Pp, KA, nblk, Q16, split;
+  int B, F, P, Pp, KA, nblk, Q16, dbg;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -64,6 +66,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -105,11 +112,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
   if (warp == 0 && lane == 0) prefetch_tmap(&prm.mapW);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < F0_NST; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&ctl->d1_full[b], 1); mbar_init(&ctl->d1_empty[b], 4);
-      mbar_init(&ctl->zb_full[b], 4); mbar_init(&ctl->zb_empty[b], 1);
-      mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 8);
-    }
+    for (int b = 0; b < F0_NZ; ++b) { mbar_init(&ctl->z_full[b], 1); mbar_init(&ctl->z_empty[b], 1); mbar_init(&ctl->zb_full[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 8); }
     mbar_init(&ctl->a_ready, 8);
     fence_barrier_init();
   }
@@ -135,125 +139,104 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     }
   } else if (warp == 1 || warp == 14) {
     // ------------------------------------------------------------------ MMA issuers: warp 1 step 1, warp 14 step 2
-    // One thread issuing both steps was the bottleneck (about 16 scalar instructions per tcgen05.mma): two
-    // independent streams, everything that does not depend on q hoisted, stage / buffer indices compile-time
-    // (F0_NST == 4 and Q % 4 == 0: slab stage = q & 3, TMEM buffer = q & 1, buffer phase = (q >> 1) & 1).
-    {
-      // all lanes run the loop (uniform control flow); the MMAs and commits of one q sit inside ONE elect.sync
-      // region, which ptxas turns into straight-line UTCHMMA issue (a lane == 0 test costs a 16-instruction
-      // per-thread loop around every tcgen05 instruction)
-      const uint32_t at_addr = smem_u32(sAt);
-      const int ksteps = KA / UMMA_K;
-      uint64_t adesc[F0_KA_MAX / UMMA_K];
+    // Two independent instruction streams coupled by mbarriers only.  All lanes run the loops (uniform control
+    // flow); the MMAs and commits of one q sit inside ONE elect.sync region, which ptxas turns into
+    // straight-line UTCHMMA issue (a lane == 0 test costs a 16-instruction per-thread loop around every
+    // tcgen05 instruction).  Slab stage = q & 3 and D buffer = q & 1 are compile-time (Q % 4 == 0); the Z
+    // buffer index runs modulo 3.
+    const uint32_t at_addr = smem_u32(sAt);
+    const int ksteps = KA / UMMA_K;
+    uint64_t adesc[F0_KA_MAX / UMMA_K];
 #pragma unroll
-      for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-        adesc[k] = umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2);
-      if (warp == 1) {
-        const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
-        const int na = ((KA / 2) + 15) & ~15;   // split point (multiple of 16; rows of 128 B: 8-row groups stay whole)
-        const uint32_t idesc1a = umma_idesc_bf16(BM, na), idesc1b = umma_idesc_bf16(BM, KA - na);
-        uint64_t wdesc[F0_NST], wk[F0_KA_MAX / UMMA_K];
+    for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+      adesc[k] = umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2);
+    int zb = 0; uint32_t zph = 0;     // Z buffer of the current q and its phase
+    if (warp == 1) {
+      const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
+      uint64_t wdesc[F0_NST], wk[F0_KA_MAX / UMMA_K];
 #pragma unroll
-        for (int s = 0; s < F0_NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * F0_SLAB_BYTES));
+      for (int s = 0; s < F0_NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * F0_SLAB_BYTES));
 #pragma unroll
-        for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
-        uint32_t it = 0;
-        for (int t = 0; t < my_tiles; ++t) {
-          mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
-          tc_fence_after();
-          for (int q = 0; q < Q; q += 4, ++it) {
+      for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
+      uint32_t it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
+        tc_fence_after();
+        for (int q = 0; q < Q; q += 4, ++it) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              mbar_wait(&ctl->full_b[u], it & 1);
-              mbar_wait(&ctl->d1_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
-              tc_fence_after();
-              if (elect_one()) {
-              const uint32_t d1 = tmem_base + (uint32_t)(F0_D1 + (u & 1) * F0_D1_STRIDE);
-              if (prm.split) {   // two independent accumulation chains (columns 0..NA-1 and NA..KA-1), interleaved
-#pragma unroll
-                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                  if (k < ksteps) {
-                    umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1a, k != 0);
-                    umma_bf16(d1 + (uint32_t)na, adesc[k], wdesc[u] + wk[k] + (uint64_t)(na * 8), idesc1b, k != 0);
-                  }
-              } else {
+          for (int u = 0; u < 4; ++u) {
+            mbar_wait(&ctl->full_b[u], it & 1);
+            mbar_wait(&ctl->z_empty[zb], zph ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t d1 = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                if (k < ksteps) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
-              }
+                if (k < ksteps && !(prm.dbg & 8)) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
               umma_commit(&ctl->empty_b[u]);
-              umma_commit(&ctl->d1_full[u & 1]);
-              }
-              __syncwarp();
+              umma_commit(&ctl->z_full[zb]);
             }
+            __syncwarp();
+            if (++zb == F0_NZ) { zb = 0; zph ^= 1; }
           }
         }
-      } else {
-        const uint32_t idesc2 = umma_idesc_bf16(BM, 128), idesc2h = umma_idesc_bf16(BM, 64);
-        for (int t = 0; t < my_tiles; ++t) {
-          mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
-          tc_fence_after();
-          for (int q = 0; q < Q; q += 4) {
+      }
+    } else {
+      const uint32_t idesc2 = umma_idesc_bf16(BM, 128);
+      for (int t = 0; t < my_tiles; ++t) {
+        mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
+        tc_fence_after();
+        for (int q = 0; q < Q; q += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              mbar_wait(&ctl->zb_full[u & 1], (uint32_t)(u >> 1));
-              mbar_wait(&ctl->d2_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
-              tc_fence_after();
-              if (elect_one()) {
+          for (int u = 0; u < 4; ++u) {
+            mbar_wait(&ctl->zb_full[zb], zph);
+            mbar_wait(&ctl->d2_empty[u & 1], (uint32_t)((u >> 1) ^ 1));
+            tc_fence_after();
+            if (elect_one()) {
               const uint32_t d2 = tmem_base + (uint32_t)(F0_D2 + (u & 1) * F0_D2_STRIDE);
-              const uint32_t zb = tmem_base + (uint32_t)(F0_ZB + (u & 1) * F0_ZB_STRIDE);
-              if (prm.split) {
-#pragma unroll
-                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                  if (k < ksteps) {
-                    umma_bf16_ts(d2, zb + (uint32_t)(k * 8), adesc[k], idesc2h, k != 0);
-                    umma_bf16_ts(d2 + 64u, zb + (uint32_t)(k * 8), adesc[k] + (uint64_t)(64 * 8), idesc2h, k != 0);
-                  }
-              } else {
+              const uint32_t za = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                if (k < ksteps) umma_bf16_ts(d2, zb + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
-              }
-              umma_commit(&ctl->zb_empty[u & 1]);
+                if (k < ksteps && !(prm.dbg & 4)) umma_bf16_ts(d2, za + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
+              umma_commit(&ctl->z_empty[zb]);        // the Z buffer (fp32 and its bf16 overlay) is free again
               umma_commit(&ctl->d2_full[u & 1]);
-              }
-              __syncwarp();
             }
+            __syncwarp();
+            if (++zb == F0_NZ) { zb = 0; zph ^= 1; }
           }
         }
       }
     }
   } else if (warp < 6) {
-    // ------------------------------------------------------------------ converters: Z fp32 -> bf16 A operand
+    // ------------------------------------------------------------------ converters: Z fp32 -> bf16, in place
+    // (the bf16 A operand of step 2 overwrites the first KA/2 columns of the fp32 Z it was made from)
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t n = 0;
+    int zb = 0; uint32_t zph = 0;
     for (int t = 0; t < my_tiles; ++t)
-      for (int q = 0; q < Q; ++q, ++n) {
-        const int buf = n & 1; const uint32_t bph = (n >> 1) & 1;
-        mbar_wait(&ctl->d1_full[buf], bph);
+      for (int q = 0; q < Q; ++q) {
+        const uint32_t zaddr = tmem_base + lane_off + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
+        mbar_wait(&ctl->z_full[zb], zph);
         tc_fence_after();
         float v[F0_KA_MAX / 16][16];
+        if (!(prm.dbg & 2)) {
 #pragma unroll
         for (int c = 0; c < F0_KA_MAX / 16; ++c)
-          if (c * 16 < KA) tmem_ld16(tmem_base + lane_off + (uint32_t)(F0_D1 + buf * F0_D1_STRIDE + c * 16), v[c]);
+          if (c * 16 < KA) tmem_ld16(zaddr + (uint32_t)(c * 16), v[c]);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->d1_empty[buf]);
-        mbar_wait(&ctl->zb_empty[buf], bph ^ 1);
-        tc_fence_after();
 #pragma unroll
         for (int c = 0; c < F0_KA_MAX / 16; ++c)
           if (c * 16 < KA) {
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) pk[j] = pack2(v[c][2 * j], v[c][2 * j + 1]);
-            tmem_st8(tmem_base + lane_off + (uint32_t)(F0_ZB + buf * F0_ZB_STRIDE + c * 8), pk);
+            tmem_st8(zaddr + (uint32_t)(c * 8), pk);
           }
         tmem_st_wait();
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->zb_full[buf]);
+        if (lane == 0) mbar_arrive(&ctl->zb_full[zb]);
+        if (++zb == F0_NZ) { zb = 0; zph ^= 1; }
       }
   } else {
     // ------------------------------------------------------------------ epilogue (+ A tile builder), 8 warps
@@ -304,6 +287,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->d2_empty[qq & 1]);
           const float bq = sbias[q0 + qq];
+          if (!(prm.dbg & 1))
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
             const float x = phi_f<ACT>((hi ? up[w] : lo[w]) + bq);
@@ -311,13 +295,11 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
           }
         }
-        if (b < prm.B) {
+        if (b < prm.B && !(prm.dbg & 17)) {
           bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
-            uint4* d = reinterpret_cast<uint4*>(dst + (int64_t)w * prm.Pp);
-            d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
-            d[1] = make_uint4(acc[w][4], acc[w][5], acc[w][6], acc[w][7]);
+            st_global_256(dst + (int64_t)w * prm.Pp, acc[w]);   // one full 32-byte sector per lane
           }
         }
       }
