@@ -121,15 +121,20 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  // Both issuing warps run their loops with all 32 lanes (uniform control flow) and put the TMA / tcgen05
+  // instructions of one stage inside ONE elect.sync region: ptxas then emits them back to back.  A `lane == 0`
+  // test instead costs a ~16-instruction per-thread loop (VOTEU / ELECT / BRA.U.ANY) around every UTCHMMA,
+  // about 170 cycles per MMA -- more than a 128x256x16 MMA takes on the tensor pipe.  elect.sync with a full
+  // mask picks the same lane every time, which tcgen05.commit relies on.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
-        const int KC = prm.k_chunks(un);
-        for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(&ctl->empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      const Unit un = prm.unit((int)blockIdx.x, (int)gridDim.x, it);
+      const int KC = prm.k_chunks(un);
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&ctl->full[stage], prm.tx_bytes());
           if constexpr (!P::kSynthA) prm.load_a(sA + stage * A_BYTES, &ctl->full[stage], un, kc);
           if constexpr (P::kBPair) {
@@ -138,47 +143,56 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
           } else {
             prm.load_b(sB + stage * B_BYTES, &ctl->full[stage], un, kc);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = prm.idesc();
-      int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
-      for (int it = 0; it < n_iters; ++it) {
-        const int KC = prm.k_chunks(prm.unit((int)blockIdx.x, (int)gridDim.x, it));
-        if constexpr (P::kBPair) {
-          static_assert(!P::kBPair || (P::kATmem && P::kAccBufs == 2 && P::kEpiWarps == 8 && P::kATiles == 1), "kBPair layout");
-          for (int kc = 0; kc < KC; ++kc) {
-            mbar_wait(&ctl->full[stage], phase);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
-            const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              if (kc == 0) { mbar_wait(&ctl->tempty[sub], bphase ^ 1); tc_fence_after(); }
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16_ts(tmem_base + (uint32_t)(sub * BN), a_tmem + (uint32_t)(k * (UMMA_K / 2)),
-                             prm.b_desc(b_addr + (uint32_t)(sub * BN * BK * 2), k), idesc, (kc | k) != 0);
-              if (kc == KC - 1) umma_commit(&ctl->tfull[sub]);
-            }
-            umma_commit(&ctl->empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-          bphase ^= 1;
-          continue;
-        }
-        mbar_wait(&ctl->tempty[buf], bphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+    const uint32_t idesc = prm.idesc();
+    int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t bphase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      const int KC = prm.k_chunks(prm.unit((int)blockIdx.x, (int)gridDim.x, it));
+      if constexpr (P::kBPair) {
+        static_assert(!P::kBPair || (P::kATmem && P::kAccBufs == 2 && P::kEpiWarps == 8 && P::kATiles == 1), "kBPair layout");
         for (int kc = 0; kc < KC; ++kc) {
           mbar_wait(&ctl->full[stage], phase);
+          if (kc == 0) mbar_wait(&ctl->tempty[0], bphase ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+          const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_ts(tmem_base, a_tmem + (uint32_t)(k * (UMMA_K / 2)), prm.b_desc(b_addr, k), idesc, (kc | k) != 0);
+            if (kc == KC - 1) umma_commit(&ctl->tfull[0]);
+          }
+          __syncwarp();
+          if (kc == 0) { mbar_wait(&ctl->tempty[1], bphase ^ 1); tc_fence_after(); }
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_ts(tmem_base + (uint32_t)BN, a_tmem + (uint32_t)(k * (UMMA_K / 2)),
+                           prm.b_desc(b_addr + (uint32_t)(BN * BK * 2), k), idesc, (kc | k) != 0);
+            if (kc == KC - 1) umma_commit(&ctl->tfull[1]);
+            umma_commit(&ctl->empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        bphase ^= 1;
+        continue;
+      }
+      mbar_wait(&ctl->tempty[buf], bphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+        if (elect_one()) {
           if constexpr (P::kATmem) {
             const uint32_t a_tmem = tmem_base + (uint32_t)(A_TMEM_BASE + stage * A_TMEM_COLS);
 #pragma unroll
@@ -194,10 +208,11 @@ __global__ void __launch_bounds__(block_threads<P>(), 1) k_tc(const __grid_const
           }
           umma_commit(&ctl->empty[stage]);              // frees the smem stage when these MMAs retire
           if (kc == KC - 1) umma_commit(&ctl->tfull[buf]);  // accumulator complete
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (P::kAccBufs == 2) { buf ^= 1; if (buf == 0) bphase ^= 1; } else { bphase ^= 1; }
     }
   } else if (warp < 2 + P::kEpiWarps) {
     // ------------------------------------------------------------------ epilogue
