@@ -79,9 +79,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 
-// Wf0[q][n = 2j+dw][k = 2i+dh] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
+// Wf0[q][n = 2j+dw][k = 2i+dh] = Wf0T[q][k][n] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
 __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restrict__ pair_i, const int* __restrict__ pair_j, int P,
-                               int KA, int KP, bf16* __restrict__ out) {
+                               int KA, int KP, bf16* __restrict__ out, bf16* __restrict__ outT) {
   const int64_t total = 4ll * P * P;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(e % P);
@@ -89,7 +89,9 @@ __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restri
     const int p = (int)(r % P), tap = (int)(r / P);
     const int dh = tap >> 1, dw = tap & 1;
     const int k = 2 * pair_i[p] + dh, n = 2 * pair_j[p] + dw;
-    out[((int64_t)q * KA + n) * KP + k] = __float2bfloat16(W0[e]);
+    const bf16 v = __float2bfloat16(W0[e]);
+    out[((int64_t)q * KA + n) * KP + k] = v;
+    if (outT) outT[((int64_t)q * KA + k) * KP + n] = v;   // transposed slabs (data gradient, conv0_dfact.cuh)
   }
 }
 

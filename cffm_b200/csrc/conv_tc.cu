@@ -716,6 +716,7 @@ __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restric
 }
 
 #include "conv0_fact.cuh"
+#include "conv0_dfact.cuh"
 
 }  // namespace tc
 
@@ -735,6 +736,8 @@ struct TCState {
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
   float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
+  bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
+  float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
   int KA = 0, nblk = 0, Q16 = 0;
   TmaEncoder enc;
 };
@@ -794,6 +797,13 @@ int tc_alloc(Model* m, bool train) {
     st->wg_partial_floats = (int64_t)max_split * 4 * Pp * Pp;
     TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
     TCTRY(tcmalloc(m, &st->bg_partial, 2 * 148 * (int64_t)m->P));
+    const char* d0 = getenv("CFFM_DGRAD0");
+    if (st->Wf0 && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
+      const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
+      TCTRY(tcmalloc(m, &st->Wf0T, n));
+      CFFM_CUDA_OK(m, cudaMemset(st->Wf0T, 0, sizeof(bf16) * (size_t)n));
+      TCTRY(tcmalloc(m, &st->pterm0, B * m->F));
+    }
   }
   return CFFM_OK;
 }
@@ -807,6 +817,8 @@ void tc_free(Model* m) {
   if (st->bg_partial) cudaFree(st->bg_partial);
   if (st->pool_part) cudaFree(st->pool_part);
   if (st->Wf0) cudaFree(st->Wf0);
+  if (st->Wf0T) cudaFree(st->Wf0T);
+  if (st->pterm0) cudaFree(st->pterm0);
   delete st;
   m->tcs = nullptr;
 }
@@ -874,6 +886,26 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   return CFFM_OK;
 }
 
+static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
+  Dgrad0FactParams p;
+  memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapWT, 0, sizeof(p.mapWT));
+  TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  TC_MAP_OK(m, mat_map(st, &p.mapWT, st->Wf0T, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  p.dY = st->dY[0]; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pterm = st->pterm0; p.g_rows = m->g_outer_rows;
+  p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_dgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, G0_SMEM));
+    attr_done = true;
+  }
+  k_pool_terms0<<<(B + 7) / 8, 256, 0, s>>>(m->outer_rows, m->v_head, B, m->F, st->pterm0);
+  int grid = (B + 7) / 8; if (grid > 148) grid = 148;
+  k_dgrad0_fact<<<grid, G0_THREADS, G0_SMEM, s>>>(p);
+  m->launches += 2;
+  CFFM_CUDA_OK(m, cudaGetLastError());
+  return CFFM_OK;
+}
+
 int tc_prep_weights(Model* m, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   CFFM_PROF(m, "prep_weights_bf16", s);
@@ -884,7 +916,7 @@ int tc_prep_weights(Model* m, cudaStream_t s) {
     m->launches++;
   }
   if (st->Wf0) {
-    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0);
+    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0, st->Wf0T);
     m->launches++;
   }
   CFFM_CUDA_OK(m, cudaGetLastError());
@@ -1011,7 +1043,9 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       const std::string tag = "conv_dgrad_l" + std::to_string(l);
       CFFM_PROF(m, tag.c_str(), s);
       Geom gd = gm; gd.tiles_n = 4 * Pp / gm.BN;
-      if (l == 0) {
+      if (l == 0 && st->Wf0T) {
+        TCTRY(dgrad0_fact_launch(m, st, B, s));
+      } else if (l == 0) {
         Conv0DgradTC p;
         p.g = gd; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
         p.g_rows = m->g_outer_rows;
