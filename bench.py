@@ -147,11 +147,11 @@ def executed_flops(spec, tag, B, precision):
     per = 2.0 * 128 * KA * (KA + 128)          # one K=KA step + one K=128 (block-diagonal) step of a (tile, channel)
     table = {"conv_fwd_l0": per, "conv_dgrad_l0": 2 * per}
     if FACT_WGRAD:
-        table["conv_wgrad_l0"] = 2.0 * 128 * KA * 256   # two K=128 steps
+        table["conv_wgrad_l0"] = 2.0 * 128 * 128 * (128 + KA)   # two K=128 steps (N = 128 and N = KA)
     return tiles * Q16 * table[tag] if tag in table else None
 
 
-FACT_WGRAD = False   # the layer-0 weight gradient still runs in direct form
+FACT_WGRAD = True    # the layer-0 weight gradient runs in factorised form as well (conv0_wfact.cuh)
 
 
 def ncu_traffic(spec, tag, B, precision):

@@ -1,0 +1,306 @@
+// Layer-0 weight gradient in factorised form (included inside namespace cffm::tc of conv_tc.cu, after conv0_dfact.cuh).
+//
+//   dWq[k, n] = sum_{b,h,w} dY0[b,h,w,q] a_{b,h}[k] a_{b,w}[n]          (Wq, a: conv0_fact.cuh)
+//             = sum_{(b,h)} A[(b,h), k] E_q[(b,h), n],   E_q[(b,h), n] = sum_w dY0[b,h,w,q] a_{b,w}[n]
+//
+//   E step   Et[n, (b,h)] = sum_{(b',w)} A[(b',w), n] Dq[(b,h),(b',w)]     SS MMA, M = n (A tile as MN-major A operand),
+//                                                                        N = 128, K = 128; Dq = block-diagonal dY0 (conv0_dfact.cuh)
+//   W step   dWq^T[n, k] += sum_{(b,h)} Et[n,(b,h)] A[(b,h), k]          TS MMA: Et converted to bf16 in place in TMEM,
+//                                                                        B = the A tile as MN-major B operand, K = 128
+// (E is produced transposed so that the contraction index of the second step runs along TMEM columns.)
+// The accumulators of 3 channels stay in TMEM while the CTA walks its share of the batch, so a unit is
+// (3 channels) x (a quarter of the tiles); CTAs that run at the same time hold neighbouring channel sets and read
+// the same 32-byte sectors of dY0 (L2 hits).  Partial sums per split are reduced in fixed order by k_wfact_reduce.
+// A unit spends only 3 channels on a tile, so the per-tile work has to be cheap: the A tiles are rows of a bf16
+// matrix A8[(b,h)][k] made once per step (k_build_a8) and arrive by TMA; builders only place the dY0 blocks.
+//
+//   warp 0       TMA: A tile of the next batch tile (double-buffered)
+//   warp 1       issues the E MMAs          warp 2   issues the W MMAs          warp 3   TMEM allocation
+//   warps 4..11  two converter sets (alternate E buffers): Et fp32 -> bf16 in place; set 0 also writes the
+//                accumulators of a finished unit to the partial sums
+//   warps 12..19 two builder groups, alternate tiles: dY0 -> diagonal blocks of Dq
+#pragma once
+
+constexpr int W0_THREADS = 640;
+constexpr int W0_QS = 3;                                   // channels per unit (3 x 80 accumulator columns + 2 x 128 for E^T)
+constexpr int W0_SPLIT_MAX = 4;                            // batch splits (fewer when the batch has fewer tiles)
+constexpr int W0_ND = 3, W0_NE = 2;
+constexpr int W0_DW = 0, W0_DW_STRIDE = 80, W0_E = 256, W0_E_STRIDE = 128;
+
+struct W0Ctl {
+  uint64_t a_ready[2], a_free[2], dq_full[W0_ND], dq_empty[W0_ND];
+  uint64_t e_full[W0_NE], e_conv[W0_NE], e_empty[W0_NE];
+  uint64_t dw_full, dw_empty, grp_done[2];
+  uint32_t tmem_base, pad;
+};
+static_assert(sizeof(W0Ctl) <= 256, "control block");
+constexpr int W0_SMEM = 1024 + 2 * G0_DQ_BYTES + W0_ND * G0_DQ_BYTES + 256;
+
+struct Wgrad0FactParams {
+  CUtensorMap mapA;          // A8 [B8*16 rows][nblk*64 cols] bf16 (B8 = batch rounded up to 8), box (64, 128)
+  const bf16* dY;            // dY0 [B][16][16][Pp]
+  float* part;               // [nsplit][Q16][KA (n)][KA (k)] fp32
+  int B, F, P, Pp, KA, nblk, Q16, nsplit;
+};
+
+// A8[(b,h)][2i+d] = o_i[b, 2h+d] in bf16, zero beyond 2F and for padded samples: the A tile of every 8-sample tile
+__global__ void k_build_a8(const float* __restrict__ rows, int B, int B8, int F, int KP, bf16* __restrict__ out) {
+  const int64_t total = (int64_t)B8 * 16 * (KP / 2);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % (KP / 2));
+    const int64_t bh = e / (KP / 2);
+    const int h = (int)(bh & 15); const int64_t b = bh >> 4;
+    float2 o = make_float2(0.f, 0.f);
+    if (i < F && b < B) o = *reinterpret_cast<const float2*>(rows + (b * F + i) * 32 + 2 * h);
+    reinterpret_cast<uint32_t*>(out)[e] = pack2(o.x, o.y);
+  }
+}
+
+// g[dh][dw][p][q] = sum over splits of part[s][q][n = 2 j_p + dw][k = 2 i_p + dh]
+__global__ void k_wfact_reduce(const float* __restrict__ part, const int* __restrict__ pair_i, const int* __restrict__ pair_j, int P,
+                               int KA, int Q16, int nsplit, float* __restrict__ g) {
+  const int64_t total = 4ll * P * P;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e % P);
+    const int64_t r = e / P;
+    const int p = (int)(r % P), tap = (int)(r / P);
+    const int k = 2 * pair_i[p] + (tap >> 1), n = 2 * pair_j[p] + (tap & 1);
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += part[(((int64_t)sp * Q16 + q) * KA + n) * KA + k];
+    g[e] = s;
+  }
+}
+
+__global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_constant__ Wgrad0FactParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sAt = smem;                                   // 2 A tiles
+  uint8_t* sDq = sAt + 2 * G0_DQ_BYTES;                  // W0_ND block-diagonal dY buffers
+  W0Ctl* ctl = reinterpret_cast<W0Ctl*>(sDq + W0_ND * G0_DQ_BYTES);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int KA = prm.KA;
+  const int n_tiles = (prm.B + 7) >> 3;
+  const int n_qs = (prm.Q16 + W0_QS - 1) / W0_QS;
+  const int n_units = n_qs * prm.nsplit;
+  const int my_units = (int)blockIdx.x < n_units ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // unit u: channel set u % n_qs, tiles [t0, t1) of split u / n_qs
+  auto unit_tiles = [&](int u, int& t0, int& t1) { const int sp = u / n_qs; t0 = sp * n_tiles / prm.nsplit; t1 = (sp + 1) * n_tiles / prm.nsplit; };
+
+  if (warp == 1 && lane == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(&ctl->a_ready[b], 1); mbar_init(&ctl->a_free[b], 1); mbar_init(&ctl->grp_done[b], 4); }
+    for (int d = 0; d < W0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4); mbar_init(&ctl->dq_empty[d], 1); }
+    for (int e = 0; e < W0_NE; ++e) {
+      mbar_init(&ctl->e_full[e], 1); mbar_init(&ctl->e_conv[e], 4); mbar_init(&ctl->e_empty[e], 1);
+    }
+    mbar_init(&ctl->dw_full, 1); mbar_init(&ctl->dw_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 3) tmem_alloc(&ctl->tmem_base, 512);
+  for (int e = threadIdx.x; e < W0_ND * G0_DQ_BYTES / 16; e += W0_THREADS) reinterpret_cast<uint4*>(sDq)[e] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA: A tiles
+    prefetch_tmap(&prm.mapA);
+    uint32_t T = 0;
+    for (int it = 0; it < my_units; ++it) {
+      int t0, t1; unit_tiles((int)blockIdx.x + it * (int)gridDim.x, t0, t1);
+      for (int t = t0; t < t1; ++t, ++T) {
+        const int ab = T & 1;
+        mbar_wait(&ctl->a_free[ab], ((T >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&ctl->a_ready[ab], (uint32_t)(prm.nblk * A_STAGE_BYTES));
+          for (int blk = 0; blk < prm.nblk; ++blk)
+            tma_load_2d(sAt + ab * G0_DQ_BYTES + blk * A_STAGE_BYTES, &prm.mapA, &ctl->a_ready[ab], blk * 64, t * BM);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ E MMAs: M = 128 (n), N = 128 (b,h), K = 128 (b',w)
+    const uint32_t at_addr = smem_u32(sAt), dq_addr = smem_u32(sDq);
+    const uint32_t idesc = umma_idesc_bf16(BM, 128, true, false);
+    uint32_t T = 0, n = 0; int d = 0; uint32_t dph = 0;
+    for (int it = 0; it < my_units; ++it) {
+      int t0, t1; unit_tiles((int)blockIdx.x + it * (int)gridDim.x, t0, t1);
+      for (int t = t0; t < t1; ++t, ++T) {
+        const int ab = T & 1;
+        mbar_wait(&ctl->a_ready[ab], (T >> 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < W0_QS; ++j, ++n) {
+          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
+          const uint32_t dq = dq_addr + (uint32_t)(d * G0_DQ_BYTES);
+          mbar_wait(&ctl->dq_full[d], dph);
+          mbar_wait(&ctl->e_empty[e], eph ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE),
+                        umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES + ks * 2048), A_STAGE_BYTES, 1024),
+                        umma_desc_k_sw128(dq + (uint32_t)((ks >> 2) * A_STAGE_BYTES)) + (uint64_t)((ks & 3) * 2), idesc, ks != 0);
+            umma_commit(&ctl->e_full[e]);
+            umma_commit(&ctl->dq_empty[d]);
+          }
+          __syncwarp();
+          if (++d == W0_ND) { d = 0; dph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ W MMAs (TS): M = 128 (n), N = KA (k), K = 128 (b,h)
+    const uint32_t at_addr = smem_u32(sAt);
+    const uint32_t idesc = umma_idesc_bf16(BM, KA, false, true);
+    uint32_t T = 0, n = 0;
+    for (int it = 0; it < my_units; ++it) {
+      int t0, t1; unit_tiles((int)blockIdx.x + it * (int)gridDim.x, t0, t1);
+      mbar_wait(&ctl->dw_empty, (uint32_t)((it & 1) ^ 1));
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++T) {
+        const int ab = T & 1;
+        for (int j = 0; j < W0_QS; ++j, ++n) {
+          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
+          mbar_wait(&ctl->e_conv[e], eph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE + ks * 8),
+                           umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES + ks * 2048), A_STAGE_BYTES, 1024), idesc,
+                           (t != t0) || ks != 0);
+            umma_commit(&ctl->e_empty[e]);
+            if (j == W0_QS - 1) umma_commit(&ctl->a_free[ab]);
+            if (j == W0_QS - 1 && t == t1 - 1) umma_commit(&ctl->dw_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // (TMEM allocation only)
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ converters: Et fp32 -> bf16 in place
+    const int set = (warp - 4) >> 2;                      // set s owns E buffer s (items with n & 1 == s)
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    uint32_t n = 0;
+    for (int it = 0; it < my_units; ++it) {
+      const int u = (int)blockIdx.x + it * (int)gridDim.x;
+      int t0, t1; unit_tiles(u, t0, t1);
+      for (int t = t0; t < t1; ++t)
+        for (int j = 0; j < W0_QS; ++j, ++n) {
+          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
+          if (e != set) continue;
+          const uint32_t ea = tmem_base + lane_off + (uint32_t)(W0_E + e * W0_E_STRIDE);
+          mbar_wait(&ctl->e_full[e], eph);
+          tc_fence_after();
+          // three passes (48 + 48 + 32 columns); pass p writes bf16 columns 24p.., whose fp32 content an earlier
+          // pass has already read
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            float v[3][16];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (pass < 2 || c < 2) tmem_ld16(ea + (uint32_t)((pass * 3 + c) * 16), v[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (pass < 2 || c < 2) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
+                tmem_st8(ea + (uint32_t)((pass * 3 + c) * 8), pk);
+              }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->e_conv[e]);
+        }
+      if (set != 0) continue;
+      // ---- unit result: 4 accumulators [k = row][n] -> partial sums of this split
+      mbar_wait(&ctl->dw_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      const int qs = u % n_qs, sp = u / n_qs;
+      for (int j = 0; j < W0_QS; ++j) {
+        const int q = qs * W0_QS + j;
+        float* dst = prm.part + ((((int64_t)sp * prm.Q16 + q) * KA + r) * KA);   // row n = r, columns k
+#pragma unroll
+        for (int c = 0; c < F0_KA_MAX / 16; ++c)
+          if (c * 16 < KA) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_off + (uint32_t)(W0_DW + j * W0_DW_STRIDE + c * 16), v);
+            tmem_ld_wait();
+            if (r < KA && q < prm.Q16) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                reinterpret_cast<float4*>(dst + c * 16)[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            }
+          }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->dw_empty);
+    }
+  } else {
+    // ------------------------------------------------------------------ builders: groups alternate tiles
+    const int grp = (warp - 12) >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const int bl = r >> 4, h = r & 15;
+    const uint32_t dq_off = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2);
+    const uint32_t dq_off2 = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2 + 1);
+    uint32_t T = 0;
+    for (int it = 0; it < my_units; ++it) {
+      const int u = (int)blockIdx.x + it * (int)gridDim.x;
+      int t0, t1; unit_tiles(u, t0, t1);
+      const int q0 = (u % n_qs) * W0_QS;
+      for (int t = t0; t < t1; ++t, ++T) {
+        if ((int)(T & 1) != grp) continue;
+        const int b = t * 8 + bl;
+        const bool ok = b < prm.B;
+        // channels q0 .. q0+2 lie inside the 8 channels that start at q0 & ~3 (two 8-byte loads per position)
+        const bf16* src = prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + (q0 & ~3);
+        uint2 dv[16], dv2[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          dv[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp)) : make_uint2(0u, 0u);
+          dv2[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp + 4)) : make_uint2(0u, 0u);
+        }
+        // ring order: the other group must have finished the previous tile's channels
+        if (T >= 1) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((T - 1) >> 1)) & 1));
+#pragma unroll
+        for (int j = 0; j < W0_QS; ++j) {
+          const uint32_t m = T * W0_QS + j;
+          const int d = m % W0_ND; const uint32_t dph = (m / W0_ND) & 1;
+          uint32_t pk[8];
+          const int ei = (q0 & 3) + j;                    // element inside the 8 loaded channels (0..5)
+          const uint32_t sel = (ei & 1) ? 0x7632 : 0x5410;
+#pragma unroll
+          for (int w = 0; w < 16; w += 2) {
+            const uint32_t a = (ei >> 1) == 0 ? dv[w].x : (ei >> 1) == 1 ? dv[w].y : dv2[w].x;
+            const uint32_t c = (ei >> 1) == 0 ? dv[w + 1].x : (ei >> 1) == 1 ? dv[w + 1].y : dv2[w + 1].x;
+            pk[w >> 1] = __byte_perm(a, c, sel);
+          }
+          mbar_wait(&ctl->dq_empty[d], dph ^ 1);
+          uint8_t* base = sDq + d * G0_DQ_BYTES;
+          *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
+        }
+        if (lane == 0) mbar_arrive(&ctl->grp_done[grp]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem_base, 512);
+}

@@ -717,6 +717,7 @@ __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restric
 
 #include "conv0_fact.cuh"
 #include "conv0_dfact.cuh"
+#include "conv0_wfact.cuh"
 
 }  // namespace tc
 
@@ -738,6 +739,8 @@ struct TCState {
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
   bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
+  float* wf_part = nullptr;      // [W0_SPLIT_MAX][Q16][KA][KA] partial sums of the factorised layer-0 weight gradient
+  bf16* A8 = nullptr;            // [B8*16][nblk*64] bf16 rows a_{b,h} (A tiles of the factorised weight gradient)
   int KA = 0, nblk = 0, Q16 = 0;
   TmaEncoder enc;
 };
@@ -804,6 +807,12 @@ int tc_alloc(Model* m, bool train) {
       CFFM_CUDA_OK(m, cudaMemset(st->Wf0T, 0, sizeof(bf16) * (size_t)n));
       TCTRY(tcmalloc(m, &st->pterm0, B * m->F));
     }
+    const char* w0 = getenv("CFFM_WGRAD0");
+    if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
+    {
+      TCTRY(tcmalloc(m, &st->wf_part, (int64_t)W0_SPLIT_MAX * st->Q16 * st->KA * st->KA));
+      TCTRY(tcmalloc(m, &st->A8, ((B + 7) / 8 * 8) * 16 * st->nblk * 64));
+    }
   }
   return CFFM_OK;
 }
@@ -819,6 +828,8 @@ void tc_free(Model* m) {
   if (st->Wf0) cudaFree(st->Wf0);
   if (st->Wf0T) cudaFree(st->Wf0T);
   if (st->pterm0) cudaFree(st->pterm0);
+  if (st->wf_part) cudaFree(st->wf_part);
+  if (st->A8) cudaFree(st->A8);
   delete st;
   m->tcs = nullptr;
 }
@@ -1019,7 +1030,28 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       }
       const int cps = (chunks_total + want - 1) / want;
       const int n_split = (chunks_total + cps - 1) / cps;
-      if (l == 0) {
+      if (l == 0 && st->wf_part) {
+        Wgrad0FactParams p;
+        const int B8 = (B + 7) / 8 * 8, KP = st->nblk * 64;
+        k_build_a8<<<148 * 4, 256, 0, s>>>(m->outer_rows, B, B8, m->F, KP, st->A8);
+        memset(&p.mapA, 0, sizeof(p.mapA));
+        TC_MAP_OK(m, mat_map(st, &p.mapA, st->A8, (int64_t)B8 * 16, KP, BM, 64));
+        p.dY = st->dY[0]; p.part = st->wf_part;
+        p.B = B; p.F = m->F; p.P = P; p.Pp = Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
+        p.nsplit = std::min(W0_SPLIT_MAX, (B + 7) / 8);
+        static bool attr_done = false;
+        if (!attr_done) {
+          CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_wgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, W0_SMEM));
+          attr_done = true;
+        }
+        const int units = (st->Q16 / W0_QS) * p.nsplit;
+        k_wgrad0_fact<<<units < 148 ? units : 148, W0_THREADS, W0_SMEM, s>>>(p);
+        const int64_t tot = 4ll * P * P;
+        int rb = (int)((tot + 255) / 256); if (rb > 148 * 8) rb = 148 * 8;
+        k_wfact_reduce<<<rb, 256, 0, s>>>(st->wf_part, m->pair_i, m->pair_j, P, st->KA, st->Q16, p.nsplit, g + m->lay.conv_w[0]);
+        m->launches += 3;
+        CFFM_CUDA_OK(m, cudaGetLastError());
+      } else if (l == 0) {
         ConvWgradTC<ACT, true> p;
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
         p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
@@ -1034,10 +1066,12 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[l], rows, Pp, 64, 64));
         TCTRY(launch_tc(m, p, tiles * n_split, s));
       }
-      const int64_t total = 4ll * P * P;
-      int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-      k_wgrad_reduce<<<blocks, 256, 0, s>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
-      m->launches++;
+      if (!(l == 0 && st->wf_part)) {
+        const int64_t total = 4ll * P * P;
+        int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+        k_wgrad_reduce<<<blocks, 256, 0, s>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
+        m->launches++;
+      }
     }
     {  // data gradient
       const std::string tag = "conv_dgrad_l" + std::to_string(l);
