@@ -256,48 +256,64 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
     const int bl = r >> 4, h = r & 15;
     const uint32_t dq_off = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2);
     const uint32_t dq_off2 = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2 + 1);
-    uint32_t T = 0;
-    for (int it = 0; it < my_units; ++it) {
-      const int u = (int)blockIdx.x + it * (int)gridDim.x;
-      int t0, t1; unit_tiles(u, t0, t1);
-      const int q0 = (u % n_qs) * W0_QS;
-      for (int t = t0; t < t1; ++t, ++T) {
-        if ((int)(T & 1) != grp) continue;
-        const int b = t * 8 + bl;
-        const bool ok = b < prm.B;
-        // channels q0 .. q0+2 lie inside the 8 channels that start at q0 & ~3 (two 8-byte loads per position)
-        const bf16* src = prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + (q0 & ~3);
-        uint2 dv[16], dv2[16];
-#pragma unroll
-        for (int w = 0; w < 16; ++w) {
-          dv[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp)) : make_uint2(0u, 0u);
-          dv2[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp + 4)) : make_uint2(0u, 0u);
-        }
-        // ring order: the other group must have finished the previous tile's channels
-        if (T >= 1) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((T - 1) >> 1)) & 1));
-#pragma unroll
-        for (int j = 0; j < W0_QS; ++j) {
-          const uint32_t m = T * W0_QS + j;
-          const int d = m % W0_ND; const uint32_t dph = (m / W0_ND) & 1;
-          uint32_t pk[8];
-          const int ei = (q0 & 3) + j;                    // element inside the 8 loaded channels (0..5)
-          const uint32_t sel = (ei & 1) ? 0x7632 : 0x5410;
-#pragma unroll
-          for (int w = 0; w < 16; w += 2) {
-            const uint32_t a = (ei >> 1) == 0 ? dv[w].x : (ei >> 1) == 1 ? dv[w].y : dv2[w].x;
-            const uint32_t c = (ei >> 1) == 0 ? dv[w + 1].x : (ei >> 1) == 1 ? dv[w + 1].y : dv2[w + 1].x;
-            pk[w >> 1] = __byte_perm(a, c, sel);
-          }
-          mbar_wait(&ctl->dq_empty[d], dph ^ 1);
-          uint8_t* base = sDq + d * G0_DQ_BYTES;
-          *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
-        }
-        if (lane == 0) mbar_arrive(&ctl->grp_done[grp]);
+    // T = index of a (unit, tile) pair in this CTA's walk; group g takes the pairs with T & 1 == g
+    auto decode = [&](uint32_t T, int& t, int& q0) -> bool {
+      uint32_t acc = 0;
+      for (int it = 0; it < my_units; ++it) {
+        const int u = (int)blockIdx.x + it * (int)gridDim.x;
+        int t0, t1; unit_tiles(u, t0, t1);
+        if (T < acc + (uint32_t)(t1 - t0)) { t = t0 + (int)(T - acc); q0 = (u % n_qs) * W0_QS; return true; }
+        acc += (uint32_t)(t1 - t0);
       }
+      return false;
+    };
+    // channels q0 .. q0+2 lie inside the two 32-bit words that start at channel q0 & ~1
+    uint32_t raw[16][2];
+    auto issue = [&](int t, int q0) {
+      const int b = t * 8 + bl;
+      const bool ok = b < prm.B;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + (q0 & ~1));
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        raw[w][0] = ok ? __ldg(src + (int64_t)w * (prm.Pp >> 1)) : 0u;
+        raw[w][1] = ok ? __ldg(src + (int64_t)w * (prm.Pp >> 1) + 1) : 0u;
+      }
+    };
+    uint32_t T = (uint32_t)grp;
+    int t, q0;
+    bool have = decode(T, t, q0);
+    if (have) issue(t, q0);
+    while (have) {
+      // the loads of this tile were issued one round ago: compress them to the three channels
+      uint32_t cur[W0_QS][8];
+#pragma unroll
+      for (int j = 0; j < W0_QS; ++j) {
+        const int ei = (q0 & 1) + j;                    // element inside the four loaded channels (0..3)
+        const uint32_t sel = (ei & 1) ? 0x7632 : 0x5410;
+#pragma unroll
+        for (int w = 0; w < 16; w += 2)
+          cur[j][w >> 1] = __byte_perm((ei >> 1) ? raw[w][1] : raw[w][0], (ei >> 1) ? raw[w + 1][1] : raw[w + 1][0], sel);
+      }
+      // next tile of this group: loads in flight while this tile's blocks are placed
+      int tn, qn;
+      const bool have_next = decode(T + 2, tn, qn);
+      if (have_next) issue(tn, qn);
+      // ring order: the other group must have finished the previous tile's channels
+      if (T >= 1) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((T - 1) >> 1)) & 1));
+#pragma unroll
+      for (int j = 0; j < W0_QS; ++j) {
+        const uint32_t m = T * W0_QS + j;
+        const int d = m % W0_ND; const uint32_t dph = (m / W0_ND) & 1;
+        mbar_wait(&ctl->dq_empty[d], dph ^ 1);
+        uint8_t* base = sDq + d * G0_DQ_BYTES;
+        *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
+        *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(cur[j][4], cur[j][5], cur[j][6], cur[j][7]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
+      }
+      if (lane == 0) mbar_arrive(&ctl->grp_done[grp]);
+      T += 2; t = tn; q0 = qn; have = have_next;
     }
   }
   tc_fence_before();
