@@ -147,7 +147,7 @@ def executed_flops(spec, tag, B, precision):
     per = 2.0 * 128 * KA * (KA + 128)          # one K=KA step + one K=128 (block-diagonal) step of a (tile, channel)
     table = {"conv_fwd_l0": per, "conv_dgrad_l0": 2 * per}
     if FACT_WGRAD:
-        table["conv_wgrad_l0"] = 2.0 * 128 * 128 * (128 + KA)   # two K=128 steps (N = 128 and N = KA)
+        table["conv_wgrad_l0"] = 2.0 * 128 * 128 * (16 + KA)   # per-sample K=16 MMAs (N=16 each) + one K=128 step (N=KA)
     return tiles * Q16 * table[tag] if tag in table else None
 
 

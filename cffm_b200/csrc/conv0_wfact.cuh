@@ -3,8 +3,8 @@
 //   dWq[k, n] = sum_{b,h,w} dY0[b,h,w,q] a_{b,h}[k] a_{b,w}[n]          (Wq, a: conv0_fact.cuh)
 //             = sum_{(b,h)} A[(b,h), k] E_q[(b,h), n],   E_q[(b,h), n] = sum_w dY0[b,h,w,q] a_{b,w}[n]
 //
-//   E step   Et[n, (b,h)] = sum_{(b',w)} A[(b',w), n] Dq[(b,h),(b',w)]     SS MMA, M = n (A tile as MN-major A operand),
-//                                                                        N = 128, K = 128; Dq = block-diagonal dY0 (conv0_dfact.cuh)
+//   E step   Et[n, (b,h)] = sum_w A[(b,w), n] dY0[b,h,w,q]                  per sample one SS MMA, M = n (A tile rows of
+//                                                                        the sample as MN-major A operand), N = 16, K = 16
 //   W step   dWq^T[n, k] += sum_{(b,h)} Et[n,(b,h)] A[(b,h), k]          TS MMA: Et converted to bf16 in place in TMEM,
 //                                                                        B = the A tile as MN-major B operand, K = 128
 // (E is produced transposed so that the contraction index of the second step runs along TMEM columns.)
@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------------ E MMAs: M = 128 (n), N = 128 (b,h), K = 128 (b',w)
     const uint32_t at_addr = smem_u32(sAt), dq_addr = smem_u32(sDq);
-    const uint32_t idesc = umma_idesc_bf16(BM, 128, true, false);
+    // The block-diagonal structure is exploited exactly: one M=128 x N=16 x K=16 MMA per sample (rows and
+    // columns b*16 .. b*16+15 of Dq, the 16 rows of the A tile that belong to sample b), no accumulation.
+    const uint32_t idesc = umma_idesc_bf16(BM, 16, true, false);
     uint32_t T = 0, n = 0; int d = 0; uint32_t dph = 0;
     for (int it = 0; it < my_units; ++it) {
       int t0, t1; unit_tiles((int)blockIdx.x + it * (int)gridDim.x, t0, t1);
@@ -133,18 +135,20 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
         const int ab = T & 1;
         mbar_wait(&ctl->a_ready[ab], (T >> 1) & 1);
         tc_fence_after();
+        // descriptors: base of the tile / buffer + a constant per sample (start-address field counts 16-byte units)
+        const uint64_t a_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
         for (int j = 0; j < W0_QS; ++j, ++n) {
           const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
-          const uint32_t dq = dq_addr + (uint32_t)(d * G0_DQ_BYTES);
+          const uint64_t b_base = umma_desc_k_sw128(dq_addr + (uint32_t)(d * G0_DQ_BYTES));
+          const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
           mbar_wait(&ctl->dq_full[d], dph);
           mbar_wait(&ctl->e_empty[e], eph ^ 1);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_bf16(tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE),
-                        umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES + ks * 2048), A_STAGE_BYTES, 1024),
-                        umma_desc_k_sw128(dq + (uint32_t)((ks >> 2) * A_STAGE_BYTES)) + (uint64_t)((ks & 3) * 2), idesc, ks != 0);
+            for (int ks = 0; ks < 8; ++ks)   // ks = sample of the tile
+              umma_bf16(et + (uint32_t)(ks * 16), a_base + (uint64_t)(ks * (2048 >> 4)),
+                        b_base + (uint64_t)((((ks >> 2) * A_STAGE_BYTES + ks * 2048) >> 4) + (ks & 3) * 2), idesc, false);
             umma_commit(&ctl->e_full[e]);
             umma_commit(&ctl->dq_empty[d]);
           }
@@ -164,16 +168,19 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++T) {
         const int ab = T & 1;
+        const uint64_t b_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
+        const bool acc0 = t != t0;
+#pragma unroll
         for (int j = 0; j < W0_QS; ++j, ++n) {
           const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
+          const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
           mbar_wait(&ctl->e_conv[e], eph);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE + ks * 8),
-                           umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES + ks * 2048), A_STAGE_BYTES, 1024), idesc,
-                           (t != t0) || ks != 0);
+              umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), et + (uint32_t)(ks * 8), b_base + (uint64_t)(ks * (2048 >> 4)), idesc,
+                           acc0 || ks != 0);
             umma_commit(&ctl->e_empty[e]);
             if (j == W0_QS - 1) umma_commit(&ctl->a_free[ab]);
             if (j == W0_QS - 1 && t == t1 - 1) umma_commit(&ctl->dw_full);
