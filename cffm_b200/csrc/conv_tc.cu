@@ -742,6 +742,7 @@ struct TCState {
   float* wf_part = nullptr;      // [W0_SPLIT_MAX][Q16][KA][KA] partial sums of the factorised layer-0 weight gradient
   bf16* A8 = nullptr;            // [B8*16][nblk*64] bf16 rows a_{b,h} (A tiles of the factorised weight gradient)
   int KA = 0, nblk = 0, Q16 = 0;
+  int fact_min_batch = 512;      // the factorised kernels have a fixed cost (they win from a few hundred samples on)
   TmaEncoder enc;
 };
 
@@ -782,7 +783,11 @@ int tc_alloc(Model* m, bool train) {
     for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
     TCTRY(tcmalloc(m, &st->pool_part, (Pp / st->BN) * B * (m->Ko >> 2)));
     const char* f0 = getenv("CFFM_FWD0");
-    if (2 * m->F <= F0_KA_MAX && !(f0 && !strcmp(f0, "direct"))) {   // factorised layer-0 forward
+    const char* mb = getenv("CFFM_FACT_MIN_BATCH");
+    const char* mf = getenv("CFFM_FACT_MIN_FIELDS");
+    if (mb) st->fact_min_batch = atoi(mb);
+    // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
+    if (2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
       st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0, n));
@@ -917,7 +922,7 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   return CFFM_OK;
 }
 
-int tc_prep_weights(Model* m, cudaStream_t s) {
+int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   CFFM_PROF(m, "prep_weights_bf16", s);
   for (int l = 0; l < m->n_live; ++l) {
@@ -926,7 +931,7 @@ int tc_prep_weights(Model* m, cudaStream_t s) {
     k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l]);
     m->launches++;
   }
-  if (st->Wf0) {
+  if (st->Wf0 && B >= st->fact_min_batch) {
     k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0, st->Wf0T);
     m->launches++;
   }
@@ -944,7 +949,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     const std::string tag = "conv_fwd_l" + std::to_string(l);
     CFFM_PROF(m, tag.c_str(), s);
     const int m_tiles = (g.M + BM - 1) / BM;
-    if (l == 0 && st->Wf0) {
+    if (l == 0 && st->Wf0 && B >= st->fact_min_batch) {
       TCTRY(fwd0_fact_launch<ACT>(m, st, B, off, s));
     } else if (l == 0) {
       ConvFwdTC<ACT, true> p;
@@ -980,7 +985,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
 }
 
 int tc_conv_forward(Model* m, int B, cudaStream_t s) {
-  int r = tc_prep_weights(m, s);
+  int r = tc_prep_weights(m, B, s);
   if (r != CFFM_OK) return r;
   CFFM_DISPATCH_ACT(m->cfg.activation, r = conv_forward_act<ACT>(m, B, s));
   return r;
@@ -1030,7 +1035,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       }
       const int cps = (chunks_total + want - 1) / want;
       const int n_split = (chunks_total + cps - 1) / cps;
-      if (l == 0 && st->wf_part) {
+      if (l == 0 && st->wf_part && B >= st->fact_min_batch) {
         Wgrad0FactParams p;
         const int B8 = (B + 7) / 8 * 8, KP = st->nblk * 64;
         k_build_a8<<<148 * 4, 256, 0, s>>>(m->outer_rows, B, B8, m->F, KP, st->A8);
@@ -1066,7 +1071,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[l], rows, Pp, 64, 64));
         TCTRY(launch_tc(m, p, tiles * n_split, s));
       }
-      if (!(l == 0 && st->wf_part)) {
+      if (!(l == 0 && st->wf_part && B >= st->fact_min_batch)) {
         const int64_t total = 4ll * P * P;
         int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
         k_wgrad_reduce<<<blocks, 256, 0, s>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
@@ -1077,7 +1082,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       const std::string tag = "conv_dgrad_l" + std::to_string(l);
       CFFM_PROF(m, tag.c_str(), s);
       Geom gd = gm; gd.tiles_n = 4 * Pp / gm.BN;
-      if (l == 0 && st->Wf0T) {
+      if (l == 0 && st->Wf0T && B >= st->fact_min_batch) {
         TCTRY(dgrad0_fact_launch(m, st, B, s));
       } else if (l == 0) {
         Conv0DgradTC p;

@@ -25,6 +25,7 @@ __global__ void k_iota(int32_t* v, int64_t n) {
 // unique + unsorted_segment_sum's summation order.
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int SEG_LT = 128;          // entries per chunk of the segmented reduction
+constexpr int SEG_SHORT_LIST = 32768; // up to this many entries: one warp per segment (k_seg_rows)
 constexpr int SEG_MAXC = 2;          // columns per lane and table (K <= 64)
 
 __global__ void k_rs_hist(const int32_t* __restrict__ keys, int n, int shift, int32_t* __restrict__ hist) {
@@ -362,6 +363,37 @@ __global__ void k_seg_fixup(const int32_t* __restrict__ sorted, int n, SparseTab
   seg_acc_apply(acc, t, key, lane, opt, lr);
 }
 
+// Short lists (the small workloads: a few thousand entries): one warp per segment, all segments in parallel.  The
+// chunked kernels above walk 128 entries per warp and apply their segments one after the other, which costs
+// ~100 us of pure latency when there are only a few dozen chunks.  Rows are added in order of appearance.
+__global__ void k_seg_rows(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start,
+                           const int32_t* __restrict__ n_uniq, int n, SparseTables t, int opt, float lr,
+                           const float* __restrict__ lr_dev) {
+  const int lane = threadIdx.x & 31;
+  const int U = *n_uniq;
+  if (lr_dev) lr = *lr_dev;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < U; sgm += nwarps) {
+    const int start = seg_start[sgm], end = sgm + 1 < U ? seg_start[sgm + 1] : n;
+    SegAcc acc; seg_acc_zero(acc);
+    for (int tb = start; tb < end; tb += 8) {     // eight gradient rows in flight (one id can fill a whole batch)
+      SegAcc rows4[8];
+      int pp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pp[u] = tb + u < end ? pos[tb + u] : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { seg_acc_zero(rows4[u]); if (tb + u < end) seg_acc_row(rows4[u], t, (int64_t)pp[u], lane); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows4[u].v[j][c];
+    }
+    seg_acc_apply(acc, t, sorted[start], lane, opt, lr);
+  }
+}
+
 // rowmap[row] = segment index for the touched rows (reset to -1 afterwards)
 __global__ void k_rowmap_set(const int32_t* __restrict__ sorted_ids, const int32_t* __restrict__ seg_start,
                              const int32_t* __restrict__ n_uniq, int32_t* __restrict__ rowmap, int clear) {
@@ -404,7 +436,11 @@ void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n,
   if (n <= 0) return;
   bool any_sparse = false, any_dense = false;
   for (int j = 0; j < 3; ++j) if (t.tab[j]) { if (t.dense[j]) any_dense = true; else any_sparse = true; }
-  if (any_sparse) {
+  if (any_sparse && n <= SEG_SHORT_LIST) {
+    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    k_seg_rows<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
+    if (launches) *launches += 1;
+  } else if (any_sparse) {
     const int chunks = (int)((n + SEG_LT - 1) / SEG_LT);
     const int blocks = (chunks * 32 + 255) / 256;
     k_seg_chunks<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, (int)n, t, opt, lr, lr_dev, w->pieces, w->chunk_flags);

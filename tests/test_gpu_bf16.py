@@ -51,8 +51,24 @@ def _pair(name, seed=3):
     return eng, ref, ids, y
 
 
+MODES = ["direct", "factorised"]
+
+
+@pytest.fixture(params=MODES)
+def layer0_mode(request, monkeypatch):
+    """Layer 0 has two implementations: the direct implicit GEMM over the synthesised cube
+    and the factorised form, which the library only picks from num_field >= 16 and batch >= 512 on.  The parity
+    cases are small, so the choice is forced here and both are held to the same tolerances."""
+    if request.param == "factorised":
+        monkeypatch.setenv("CFFM_FACT_MIN_BATCH", "1")
+        monkeypatch.setenv("CFFM_FACT_MIN_FIELDS", "1")
+    else:
+        monkeypatch.setenv("CFFM_FACT_MIN_BATCH", "1000000000")
+    return request.param
+
+
 @pytest.mark.parametrize("name", list(SHAPES))
-def test_bf16_forward(name):
+def test_bf16_forward(name, layer0_mode):
     eng, ref, ids, y = _pair(name)
     out = eng.forward(ids)
     want, inter = ref.forward(ids, return_intermediates=True)
@@ -67,7 +83,7 @@ def test_bf16_forward(name):
 
 
 @pytest.mark.parametrize("name", list(SHAPES))
-def test_bf16_gradients(name):
+def test_bf16_gradients(name, layer0_mode):
     eng, ref, ids, y = _pair(name)
     l_ref, dense, sparse = ref.gradients(ids, y)
     loss = eng.train_step(ids, y)

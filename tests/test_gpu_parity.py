@@ -217,14 +217,15 @@ def test_gather_is_bit_exact():
         assert torch.equal(out, table[ids.long()])
 
 
-def test_sparse_adagrad_operator():
+@pytest.mark.parametrize("n", [20000, 60000])   # short list: one warp per segment; long list: chunked reduction
+def test_sparse_adagrad_operator(n):
     """Sort-by-row + segmented sum + SparseApplyAdagrad: unique rows bit exact, untouched rows
     bitwise unchanged, touched rows equal to the fp32 restatement of the kernel's (deterministic) summation order."""
     from cffm_b200 import _lib
     import ctypes as C
     lib = _lib.load()
     rng = np.random.default_rng(1)
-    M, K, n, lr = 3000, 32, 20000, 0.05
+    M, K, lr = 3000, 32, 0.05
     tab = rng.standard_normal((M, K)).astype(np.float32)
     acc = np.full((M, K), 1e-8, dtype=np.float32)
     ids = np.minimum((rng.pareto(1.0, n) * 3).astype(np.int64), M - 1).astype(np.int32)  # heavy duplication
@@ -242,12 +243,14 @@ def test_sparse_adagrad_operator():
     uniq = np.unique(ids)
     assert int(nu_d.item()) == len(uniq)
     assert np.array_equal(u_d[: len(uniq)].cpu().numpy(), uniq)
-    # the kernel's summation order, restated: the stably sorted list is cut into chunks of 128 entries; inside a
-    # chunk a row's gradient rows are added in order of appearance, then the chunk pieces in chunk order (fp32)
+    # the kernel's summation order, restated.  Up to 32768 entries: a row's gradient rows in order of appearance.
+    # Longer lists: the stably sorted list is cut into chunks of 128 entries; inside a chunk a row's gradient rows
+    # are added in order of appearance, then the chunk pieces in chunk order (fp32)
     order = np.argsort(ids, kind="stable")
+    chunk_len = 128 if n > 32768 else n
     pieces = {}
     for t, src in enumerate(order):
-        key = (int(ids[src]), t // 128)
+        key = (int(ids[src]), t // chunk_len)
         pieces[key] = pieces.get(key, np.zeros(K, dtype=np.float32)) + grads[src]
     G = np.zeros((M, K), dtype=np.float32)
     for (row, chunk) in sorted(pieces):
