@@ -8,10 +8,10 @@
 //   W step   dWq^T[n, k] += sum_{(b,h)} Et[n,(b,h)] A[(b,h), k]          TS MMA: Et converted to bf16 in place in TMEM,
 //                                                                        B = the A tile as MN-major B operand, K = 128
 // (E is produced transposed so that the contraction index of the second step runs along TMEM columns.)
-// The accumulators of 3 channels stay in TMEM while the CTA walks its share of the batch, so a unit is
-// (3 channels) x (a quarter of the tiles); CTAs that run at the same time hold neighbouring channel sets and read
+// The accumulators of 4 channels stay in TMEM while the CTA walks its share of the batch, so a unit is
+// (4 channels) x (a third of the tiles); CTAs that run at the same time hold neighbouring channel sets and read
 // the same 32-byte sectors of dY0 (L2 hits).  Partial sums per split are reduced in fixed order by k_wfact_reduce.
-// A unit spends only 3 channels on a tile, so the per-tile work has to be cheap: the A tiles are rows of a bf16
+// A unit spends only 4 channels on a tile, so the per-tile work has to be cheap: the A tiles are rows of a bf16
 // matrix A8[(b,h)][k] made once per step (k_build_a8) and arrive by TMA; builders only place the dY0 blocks.
 //
 //   warp 0       TMA: A tile of the next batch tile (double-buffered)
@@ -22,10 +22,11 @@
 #pragma once
 
 constexpr int W0_THREADS = 640;
-constexpr int W0_QS = 3;                                   // channels per unit (3 x 80 accumulator columns + 2 x 128 for E^T)
-constexpr int W0_SPLIT_MAX = 4;                            // batch splits (fewer when the batch has fewer tiles)
-constexpr int W0_ND = 3, W0_NE = 2;
-constexpr int W0_DW = 0, W0_DW_STRIDE = 80, W0_E = 256, W0_E_STRIDE = 128;
+constexpr int W0_QS = 4;                                   // channels per unit: one aligned 8-byte load per position;
+                                                           // 4 x 80 accumulator columns + 3 x 64 for E^T = 512 TMEM columns
+constexpr int W0_SPLIT_MAX = 3;                            // batch splits (fewer when the batch has fewer tiles)
+constexpr int W0_ND = 3, W0_NE = 3;                        // Dq buffers; E buffers (an item = half a tile = 4 samples = 64 columns)
+constexpr int W0_DW = 0, W0_DW_STRIDE = 80, W0_E = 320, W0_E_STRIDE = 64;
 
 struct W0Ctl {
   uint64_t a_ready[2], a_free[2], dq_full[W0_ND], dq_empty[W0_ND];
@@ -137,22 +138,27 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
         tc_fence_after();
         // descriptors: base of the tile / buffer + a constant per sample (start-address field counts 16-byte units)
         const uint64_t a_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
-        for (int j = 0; j < W0_QS; ++j, ++n) {
-          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
+        for (int j = 0; j < W0_QS; ++j) {
           const uint64_t b_base = umma_desc_k_sw128(dq_addr + (uint32_t)(d * G0_DQ_BYTES));
-          const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
           mbar_wait(&ctl->dq_full[d], dph);
-          mbar_wait(&ctl->e_empty[e], eph ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)   // ks = sample of the tile
-              umma_bf16(et + (uint32_t)(ks * 16), a_base + (uint64_t)(ks * (2048 >> 4)),
-                        b_base + (uint64_t)((((ks >> 2) * A_STAGE_BYTES + ks * 2048) >> 4) + (ks & 3) * 2), idesc, false);
-            umma_commit(&ctl->e_full[e]);
-            umma_commit(&ctl->dq_empty[d]);
+          for (int hf = 0; hf < 2; ++hf, ++n) {   // an item is half a tile: 4 samples, 64 columns of E^T
+            const int e = n % W0_NE; const uint32_t eph = (n / W0_NE) & 1;
+            const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
+            mbar_wait(&ctl->e_empty[e], eph ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int sb = 0; sb < 4; ++sb) {
+                const int ks = hf * 4 + sb;         // sample of the tile
+                umma_bf16(et + (uint32_t)(sb * 16), a_base + (uint64_t)(ks * (2048 >> 4)),
+                          b_base + (uint64_t)((((ks >> 2) * A_STAGE_BYTES + ks * 2048) >> 4) + (ks & 3) * 2), idesc, false);
+              }
+              umma_commit(&ctl->e_full[e]);
+              if (hf == 1) umma_commit(&ctl->dq_empty[d]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++d == W0_ND) { d = 0; dph ^= 1; }
         }
       }
@@ -171,21 +177,24 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
         const uint64_t b_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
         const bool acc0 = t != t0;
 #pragma unroll
-        for (int j = 0; j < W0_QS; ++j, ++n) {
-          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
-          const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
-          mbar_wait(&ctl->e_conv[e], eph);
-          tc_fence_after();
-          if (elect_one()) {
+        for (int j = 0; j < W0_QS; ++j) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), et + (uint32_t)(ks * 8), b_base + (uint64_t)(ks * (2048 >> 4)), idesc,
-                           acc0 || ks != 0);
-            umma_commit(&ctl->e_empty[e]);
-            if (j == W0_QS - 1) umma_commit(&ctl->a_free[ab]);
-            if (j == W0_QS - 1 && t == t1 - 1) umma_commit(&ctl->dw_full);
+          for (int hf = 0; hf < 2; ++hf, ++n) {
+            const int e = n % W0_NE; const uint32_t eph = (n / W0_NE) & 1;
+            const uint32_t et = tmem_base + (uint32_t)(W0_E + e * W0_E_STRIDE);
+            mbar_wait(&ctl->e_conv[e], eph);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int sb = 0; sb < 4; ++sb)
+                umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), et + (uint32_t)(sb * 8),
+                             b_base + (uint64_t)((hf * 4 + sb) * (2048 >> 4)), idesc, acc0 || hf != 0 || sb != 0);
+              umma_commit(&ctl->e_empty[e]);
+              if (j == W0_QS - 1 && hf == 1) umma_commit(&ctl->a_free[ab]);
+              if (j == W0_QS - 1 && hf == 1 && t == t1 - 1) umma_commit(&ctl->dw_full);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
     // (TMEM allocation only)
   } else if (warp < 12) {
     // ------------------------------------------------------------------ converters: Et fp32 -> bf16 in place
-    const int set = (warp - 4) >> 2;                      // set s owns E buffer s (items with n & 1 == s)
+    const int set = (warp - 4) >> 2;                      // two sets, alternate items
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -202,29 +211,26 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       const int u = (int)blockIdx.x + it * (int)gridDim.x;
       int t0, t1; unit_tiles(u, t0, t1);
       for (int t = t0; t < t1; ++t)
-        for (int j = 0; j < W0_QS; ++j, ++n) {
-          const int e = n & 1; const uint32_t eph = (n >> 1) & 1;
-          if (e != set) continue;
+        for (int j = 0; j < 2 * W0_QS; ++j, ++n) {        // items: (channel, half tile)
+          if ((int)(n & 1) != set) continue;              // the sets take alternate items
+          const int e = n % W0_NE; const uint32_t eph = (n / W0_NE) & 1;
           const uint32_t ea = tmem_base + lane_off + (uint32_t)(W0_E + e * W0_E_STRIDE);
           mbar_wait(&ctl->e_full[e], eph);
           tc_fence_after();
-          // three passes (48 + 48 + 32 columns); pass p writes bf16 columns 24p.., whose fp32 content an earlier
-          // pass has already read
+          // two passes of 32 columns; pass p writes bf16 columns 16p.., whose fp32 content has been read
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            float v[3][16];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              if (pass < 2 || c < 2) tmem_ld16(ea + (uint32_t)((pass * 3 + c) * 16), v[c]);
+          for (int pass = 0; pass < 2; ++pass) {
+            float v[2][16];
+            tmem_ld16(ea + (uint32_t)(pass * 32), v[0]);
+            tmem_ld16(ea + (uint32_t)(pass * 32 + 16), v[1]);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              if (pass < 2 || c < 2) {
-                uint32_t pk[8];
+            for (int c = 0; c < 2; ++c) {
+              uint32_t pk[8];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
-                tmem_st8(ea + (uint32_t)((pass * 3 + c) * 8), pk);
-              }
+              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
+              tmem_st8(ea + (uint32_t)(pass * 16 + c * 8), pk);
+            }
           }
           tmem_st_wait();
           tc_fence_before();
@@ -274,17 +280,14 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       }
       return false;
     };
-    // channels q0 .. q0+2 lie inside the two 32-bit words that start at channel q0 & ~1
-    uint32_t raw[16][2];
+    // channels q0 .. q0+3 (q0 = 4 * set index): one aligned 8-byte load per position
+    uint2 raw[16];
     auto issue = [&](int t, int q0) {
       const int b = t * 8 + bl;
       const bool ok = b < prm.B;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + (q0 & ~1));
+      const bf16* src = prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + q0;
 #pragma unroll
-      for (int w = 0; w < 16; ++w) {
-        raw[w][0] = ok ? __ldg(src + (int64_t)w * (prm.Pp >> 1)) : 0u;
-        raw[w][1] = ok ? __ldg(src + (int64_t)w * (prm.Pp >> 1) + 1) : 0u;
-      }
+      for (int w = 0; w < 16; ++w) raw[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp)) : make_uint2(0u, 0u);
     };
     uint32_t T = (uint32_t)grp;
     int t, q0;
@@ -295,11 +298,10 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       uint32_t cur[W0_QS][8];
 #pragma unroll
       for (int j = 0; j < W0_QS; ++j) {
-        const int ei = (q0 & 1) + j;                    // element inside the four loaded channels (0..3)
-        const uint32_t sel = (ei & 1) ? 0x7632 : 0x5410;
+        const uint32_t sel = (j & 1) ? 0x7632 : 0x5410;
 #pragma unroll
         for (int w = 0; w < 16; w += 2)
-          cur[j][w >> 1] = __byte_perm((ei >> 1) ? raw[w][1] : raw[w][0], (ei >> 1) ? raw[w + 1][1] : raw[w + 1][0], sel);
+          cur[j][w >> 1] = __byte_perm((j >> 1) ? raw[w].y : raw[w].x, (j >> 1) ? raw[w + 1].y : raw[w + 1].x, sel);
       }
       // next tile of this group: loads in flight while this tile's blocks are placed
       int tn, qn;
