@@ -267,7 +267,7 @@ __global__ void k_inner_linear_bwd(const InnerLinBwdArgs a) {
     const int PK = P * K;
     const int nph = K >= 32 ? 1 : 32 / K;
     float gw0 = 0.f, gw1 = 0.f, gc = 0.f;
-    for (int base = 0; base < PK; base += 32) {
+    auto pass = [&](int base, float wdv) {
       const int idx = base + lane;
       const bool ok = idx < PK;
       float I = 0.f, ei = 0.f, ej = 0.f;
@@ -281,7 +281,7 @@ __global__ void k_inner_linear_bwd(const InnerLinBwdArgs a) {
       const float Ao = __shfl_xor_sync(0xffffffffu, A, 1);
       const float a0 = o ? Ao : A, a1 = o ? A : Ao;
       const float y = fmaf(a1, wt1, a0 * wt0) + cbo;
-      const float dR = ok ? g * __ldg(a.Wd + idx) : 0.f;
+      const float dR = ok ? g * wdv : 0.f;
       const float dYv = dR * phi_df<ACT>(y);
       gw0 = fmaf(dYv, a0, gw0); gw1 = fmaf(dYv, a1, gw1); gc += dYv;
       const float dYo = __shfl_xor_sync(0xffffffffu, dYv, 1);
@@ -297,6 +297,23 @@ __global__ void k_inner_linear_bwd(const InnerLinBwdArgs a) {
           __syncwarp();
         }
       }
+    };
+    // The dense-layer weight of an element is the only global load of a pass and everything depends on it:
+    // fetch it four passes (128 elements) ahead so that its latency is off the loop-carried path.
+    float wn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i2 = u * 32 + lane; wn[u] = i2 < PK ? __ldg(a.Wd + i2) : 0.f; }
+    for (int base = 0; base < PK; base += 128) {
+      float wc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        wc[u] = wn[u];
+        const int i2 = base + 128 + u * 32 + lane;
+        wn[u] = i2 < PK ? __ldg(a.Wd + i2) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + u * 32 < PK) pass(base + u * 32, wc[u]);
     }
 #pragma unroll
     for (int off = 16; off > 1; off >>= 1) {
@@ -376,7 +393,8 @@ __global__ void k_inner_dense_grad(const InnerDenseGradArgs a) {
   const int rpc = (a.B + a.C - 1) / a.C;
   const int b0 = c * rpc, b1 = min(a.B, b0 + rpc);
   float s = 0.f;
-  for (int b = b0; b < b1; ++b) {
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {   // two dependent loads per sample (id, then row): keep four samples in flight
     float A = 0.f;
     if (ok) {
       const float ei = __ldg(a.tab + (int64_t)__ldg(a.ids + (int64_t)b * F + fi) * K + k);
