@@ -24,7 +24,7 @@ __global__ void k_iota(int32_t* v, int64_t n) {
 // Equal ids keep their order of appearance, which is what makes the segmented sum below reproduce
 // unique + unsorted_segment_sum's summation order.
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
-constexpr int SEG_LT = 128;          // entries per chunk of the segmented reduction
+constexpr int SEG_LT = 32;           // entries per chunk of the segmented reduction (one warp each: short chunks = more warps in flight)
 constexpr int SEG_SHORT_LIST = 32768; // up to this many entries: one warp per segment (k_seg_rows)
 constexpr int SEG_MAXC = 2;          // columns per lane and table (K <= 64)
 

@@ -244,10 +244,10 @@ def test_sparse_adagrad_operator(n):
     assert int(nu_d.item()) == len(uniq)
     assert np.array_equal(u_d[: len(uniq)].cpu().numpy(), uniq)
     # the kernel's summation order, restated.  Up to 32768 entries: a row's gradient rows in order of appearance.
-    # Longer lists: the stably sorted list is cut into chunks of 128 entries; inside a chunk a row's gradient rows
+    # Longer lists: the stably sorted list is cut into chunks of 32 entries; inside a chunk a row's gradient rows
     # are added in order of appearance, then the chunk pieces in chunk order (fp32)
     order = np.argsort(ids, kind="stable")
-    chunk_len = 128 if n > 32768 else n
+    chunk_len = 32 if n > 32768 else n
     pieces = {}
     for t, src in enumerate(order):
         key = (int(ids[src]), t // chunk_len)
