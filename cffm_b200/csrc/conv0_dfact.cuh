@@ -44,8 +44,18 @@ struct Dgrad0FactParams {
   const float* v_head;       // pooling weights of level 0: v[0..31]
   const float2* pterm;       // [B][F]: (sum_{j>f} S_j, sum_{i<f} T_i), S_j = sum_c o_j[c], T_i = sum_a v[a] o_i[a]
   float* g_rows;             // [B][F][32]
+  float* bpart;              // [tiles][4 warps][Q16]: column sums of dY0 per builder warp (bias gradient of layer 0)
   int B, F, P, Pp, KA, nblk, Q16;
 };
+
+// d b_0[q] = sum over tiles and builder warps (fixed order) of the column sums collected by k_dgrad0_fact
+__global__ void k_dfact_bias_reduce(const float* __restrict__ bpart, int rows, int Q16, int P, float* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += bpart[(int64_t)r * Q16 + q];
+  out[q] = s;
+}
 
 // pooling term of the layer-0 data gradient, per sample and field (see Dgrad0FactParams::pterm)
 __global__ void k_pool_terms0(const float* __restrict__ rows, const float* __restrict__ v, int B, int F, float2* __restrict__ out) {
@@ -300,6 +310,19 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
 #pragma unroll
         for (int w = 0; w < 16; ++w)
           dv[w] = b < prm.B ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)w * prm.Pp + q0)) : make_uint4(0u, 0u, 0u, 0u);
+        {  // d b_0[q] = sum of dY0 over all positions: this warp's 32 rows x 16 w of the 8 channels (the data is here anyway)
+          float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int w = 0; w < 16; ++w) {
+            const uint32_t wv[4] = {dv[w].x, dv[w].y, dv[w].z, dv[w].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { cs[2 * j] += __uint_as_float(wv[j] << 16); cs[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u); }
+          }
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float v = warp_sum(cs[j]); if (lane == j) mine = v; }
+          if (lane < 8) prm.bpart[((int64_t)tile * 4 + (warp & 3)) * Q + q0 + lane] = mine;
+        }
         // The groups take the 8-channel groups alternately and must fill the Dq ring in channel order (a parity
         // wait cannot tell one ring revolution from the next): wait until the other group has finished the
         // preceding 8 channels.  n >> 3 = index of this 8-channel group over the whole kernel.

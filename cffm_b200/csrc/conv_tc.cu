@@ -738,6 +738,7 @@ struct TCState {
   float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
   bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
+  float* df_bpart = nullptr;     // [tiles][4][Q16] column sums of dY0 collected by the factorised data gradient
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
   float* wf_part = nullptr;      // [W0_SPLIT_MAX][Q16][KA][KA] partial sums of the factorised layer-0 weight gradient
   bf16* A8 = nullptr;            // [B8*16][nblk*64] bf16 rows a_{b,h} (A tiles of the factorised weight gradient)
@@ -811,6 +812,7 @@ int tc_alloc(Model* m, bool train) {
       TCTRY(tcmalloc(m, &st->Wf0T, n));
       CFFM_CUDA_OK(m, cudaMemset(st->Wf0T, 0, sizeof(bf16) * (size_t)n));
       TCTRY(tcmalloc(m, &st->pterm0, B * m->F));
+      TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));
     }
     const char* w0 = getenv("CFFM_WGRAD0");
     if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
@@ -833,6 +835,7 @@ void tc_free(Model* m) {
   if (st->Wf0) cudaFree(st->Wf0);
   if (st->Wf0T) cudaFree(st->Wf0T);
   if (st->pterm0) cudaFree(st->pterm0);
+  if (st->df_bpart) cudaFree(st->df_bpart);
   if (st->wf_part) cudaFree(st->wf_part);
   if (st->A8) cudaFree(st->A8);
   delete st;
@@ -908,6 +911,7 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
   TC_MAP_OK(m, mat_map(st, &p.mapWT, st->Wf0T, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
   p.dY = st->dY[0]; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pterm = st->pterm0; p.g_rows = m->g_outer_rows;
+  p.bpart = st->df_bpart;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
   static bool attr_done = false;
   if (!attr_done) {
@@ -917,7 +921,9 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   k_pool_terms0<<<(B + 7) / 8, 256, 0, s>>>(m->outer_rows, m->v_head, B, m->F, st->pterm0);
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
   k_dgrad0_fact<<<grid, G0_THREADS, G0_SMEM, s>>>(p);
-  m->launches += 2;
+  // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
+  k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * 4, st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
+  m->launches += 3;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
 }
@@ -1009,7 +1015,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
   for (int l = m->n_live - 1; l >= 0; --l) {
     const Geom gm = make_geom(m, st, B, l);
     const int64_t rows = gm.M;
-    {  // bias gradient
+    if (!(l == 0 && st->Wf0T && B >= st->fact_min_batch)) {  // bias gradient (layer 0, factorised: collected by k_dgrad0_fact)
       CFFM_PROF(m, "colsum", s);
       const int C = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
       const int CG = Pp / 8;
