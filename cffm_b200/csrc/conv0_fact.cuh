@@ -39,11 +39,14 @@ struct F0Ctl {
   uint64_t a_ready;
   uint32_t tmem_base, pad;
 };
-constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4;
+constexpr int F0_STAGE_BYTES = 8 * 32 * 32;   // per epilogue warp: [8 w][32 rows][16 channels] bf16
+constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
 static_assert(sizeof(F0Ctl) <= 256, "control block");
 
 struct Fwd0FactParams {
   CUtensorMap mapW;     // Wf0 viewed as [Q16*KA rows][nblk*64 cols] bf16, box (64, KA)
+  CUtensorMap mapX;     // X1 as (q: Pp, row = b*16+h: B*16, w: 16), dense box (16, 32, 8) for the epilogue's TMA stores
+  int tma_store;        // 0: the tensor map could not be encoded, lanes store their sectors themselves
   const float* rows;    // outer rows [B][F][32]
   const float* bias;
   bf16* Xout;           // X1 [B][16][16][Pp]
@@ -251,6 +254,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     const bool hi = (lane & 16) != 0;             // second sample of this warp: its block starts 16 columns later
     const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32 + grp * 8);
     float* xch = sbias + F0_BIAS_MAX;             // pooling sums of group 1, [2][128]
+    // staging tile of this warp for the TMA store (128-byte aligned, after xch)
+    uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xch + 2 * BM) + 127) & ~(uintptr_t)127) + ew * F0_STAGE_BYTES;
     auto build_a = [&](int tile) {
       const int b = tile * 8 + (r >> 4);
       const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
@@ -297,7 +302,21 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
           }
         }
-        if (b < prm.B && !(prm.dbg & 17)) {
+        if (prm.tma_store && !(prm.dbg & 17)) {
+          // 32 rows x 8 w x 16 channels of this warp -> staging tile -> one TMA store (rows beyond the batch are
+          // clipped by the tensor map); the copy engine does the scattered 32-byte writes, not the LSU
+          if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
+          __syncwarp();
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            uint4* d = reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 32);
+            d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+            d[1] = make_uint4(acc[w][4], acc[w][5], acc[w][6], acc[w][7]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
+        } else if (b < prm.B && !(prm.dbg & 17)) {
           bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
       // every MMA of this tile has retired (the last step-2 result was read above): the A tile may be rebuilt
       if (t + 1 < my_tiles) build_a(tile + (int)gridDim.x);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();

@@ -889,6 +889,14 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   Fwd0FactParams p;
   memset(&p.mapW, 0, sizeof(p.mapW));
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16, 32, 8) TMA stores
+    const uint64_t dims[3] = {(uint64_t)st->Pp, (uint64_t)B * 16, 16};
+    const uint64_t str[2] = {(uint64_t)16 * st->Pp * 2, (uint64_t)st->Pp * 2};
+    const uint32_t box[3] = {16, 32, 8};
+    const char* e = getenv("CFFM_F0_TMASTORE");
+    p.tma_store = !(e && !strcmp(e, "0")) && st->enc.encode_bf16(&p.mapX, st->X[1], 3, dims, str, box, false) ? 1 : 0;
+    if (!p.tma_store) memset(&p.mapX, 0, sizeof(p.mapX));
+  }
   p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;

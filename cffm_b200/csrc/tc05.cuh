@@ -185,6 +185,15 @@ __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t leader) {
       "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(leader)
       : "memory");
 }
+// TMA store of a dense 3-D box from shared memory (bulk async group); OOB parts of the box are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // mbarrier arrive when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -211,7 +220,7 @@ struct TmaEncoder {
   bool init();
   // bf16 tensor, dims[0] fastest; strides_bytes[i] = stride of dims[i+1]; box[0]*2 bytes must be 128 (SWIZZLE_128B)
   bool encode_bf16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) const;
+                   const uint32_t* box, bool swizzle128 = true) const;   // swizzle128 = false: dense box (TMA stores)
 };
 
 }  // namespace cffm
