@@ -1,8 +1,11 @@
 // Tensor-core (tcgen05) conv stack for CFFM_PREC_BF16: the 2x2/stride-2 conv layers of the outer
 // path (CFFM.py:373-391) as implicit GEMMs with bf16 operands and fp32 accumulation in TMEM.
 //
-//   layer 0   A operand = interaction cube (CFFM.py:355-367), synthesised by four producer warps
-//             straight into the UMMA shared-memory layout; it never exists in HBM.
+//   layer 0   factorised form (conv0_fact.cuh, conv0_dfact.cuh, conv0_wfact.cuh: the cube is rank one per pair,
+//             so the layer is a bilinear form in the rows themselves) from 16 fields / 512 samples on; otherwise
+//             the direct form below: A operand = interaction cube (CFFM.py:355-367), synthesised by producer
+//             warps straight into tensor memory / the UMMA shared-memory layout.  Either way the cube never
+//             exists in HBM.
 //   layer >=1 A operand = im2col view of the stored activations: non-overlapping 2x2 windows make
 //             im2col a pure re-index, expressed as a 5-D TMA box over the NHWC tensor.
 //   epilogues read the accumulator from TMEM and fuse bias + relu + activation + bf16 store +
