@@ -62,18 +62,26 @@ __global__ void k_pool_terms0(const float* __restrict__ rows, const float* __res
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const float vl = v[lane];
-  float2* o = out + (int64_t)b * F;
+  // lane holds S_f, T_f of fields f = lane and f = lane + 32 (F <= 48)
+  float S0 = 0.f, T0 = 0.f, S1 = 0.f, T1 = 0.f;
   for (int f = 0; f < F; ++f) {
     const float x = rows[((int64_t)b * F + f) * 32 + lane];
-    const float s = warp_sum(x), t = warp_sum(x * vl);
-    if (lane == 0) o[f] = make_float2(s, t);
+    const float sv = warp_sum(x), tv = warp_sum(x * vl);
+    if ((f & 31) == lane) { if (f < 32) { S0 = sv; T0 = tv; } else { S1 = sv; T1 = tv; } }
   }
-  if (lane == 0) {   // exclusive prefix of T, exclusive suffix of S (F <= 48)
-    float pre = 0.f;
-    for (int f = 0; f < F; ++f) { const float t = o[f].y; o[f].y = pre; pre += t; }
-    float suf = 0.f;
-    for (int f = F - 1; f >= 0; --f) { const float sv = o[f].x; o[f].x = suf; suf += sv; }
+  // inclusive scans over the lanes, then exclusive prefix of T and exclusive suffix of S over the fields
+  float iS0 = S0, iT0 = T0, iS1 = S1, iT1 = T1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float a0 = __shfl_up_sync(0xffffffffu, iS0, o), a1 = __shfl_up_sync(0xffffffffu, iT0, o);
+    const float a2 = __shfl_up_sync(0xffffffffu, iS1, o), a3 = __shfl_up_sync(0xffffffffu, iT1, o);
+    if (lane >= o) { iS0 += a0; iT0 += a1; iS1 += a2; iT1 += a3; }
   }
+  const float totS0 = __shfl_sync(0xffffffffu, iS0, 31), totT0 = __shfl_sync(0xffffffffu, iT0, 31);
+  const float totS1 = __shfl_sync(0xffffffffu, iS1, 31);
+  float2* o = out + (int64_t)b * F;
+  if (lane < F) o[lane] = make_float2(totS1 + (totS0 - iS0), iT0 - T0);
+  if (lane + 32 < F) o[lane + 32] = make_float2(totS1 - iS1, totT0 + (iT1 - T1));
 }
 
 __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_constant__ Dgrad0FactParams prm) {

@@ -942,7 +942,9 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
 int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   CFFM_PROF(m, "prep_weights_bf16", s);
-  for (int l = 0; l < m->n_live; ++l) {
+  // layer 0: the direct kernels' bf16 copies are not needed when every layer-0 kernel of this call is the factorised one
+  const bool fact0 = st->Wf0 && B >= st->fact_min_batch && (!st->dY[0] || (st->Wf0T && st->wf_part));
+  for (int l = fact0 ? 1 : 0; l < m->n_live; ++l) {
     const int64_t total = 4ll * st->Pp * st->Pp;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
     k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l]);
