@@ -685,11 +685,13 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   int64_t n_upd = (int64_t)B * F;
   if (m->world > 1) {
     CFFM_PROF(m, "dp_allreduce_allgather", s);
-    int r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) return r;
-    r = comm_allgather(m, ids, m->all_ids, sizeof(int32_t) * n_upd, s); if (r != CFFM_OK) return r;
+    int r = comm_group_begin(m); if (r != CFFM_OK) return r;
+    r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
+    r = comm_allgather(m, ids, m->all_ids, sizeof(int32_t) * n_upd, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
     if (m->cfg.inner_conv) { r = comm_allgather(m, gi, m->all_g_inner, sizeof(float) * n_upd * m->Ki, s); if (r != CFFM_OK) return r; }
     if (m->cfg.outer_conv) { r = comm_allgather(m, go, m->all_g_outer, sizeof(float) * n_upd * m->Ko, s); if (r != CFFM_OK) return r; }
-    r = comm_allgather(m, gbr, m->all_g_bias, sizeof(float) * n_upd, s); if (r != CFFM_OK) return r;
+    r = comm_allgather(m, gbr, m->all_g_bias, sizeof(float) * n_upd, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
+    r = comm_group_end(m); if (r != CFFM_OK) return r;
     upd_ids = m->all_ids; gi = m->all_g_inner; go = m->all_g_outer; gbr = m->all_g_bias;
     n_upd *= m->world;
   }

@@ -20,6 +20,8 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
 };
 
 static NcclApi g_nccl;
@@ -40,6 +42,8 @@ static bool nccl_load() {
   SYM(AllReduce, "ncclAllReduce");
   SYM(AllGather, "ncclAllGather");
   SYM(GetErrorString, "ncclGetErrorString");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
 #undef SYM
   g_nccl.lib = lib;
   return true;
@@ -60,6 +64,20 @@ int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_ran
   ncclResult_t r = g_nccl.AllGather(send, recv, (size_t)bytes_per_rank, ncclInt8, m->comm->comm, s);
   if (r != ncclSuccess) { m->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
   m->launches++;
+  return CFFM_OK;
+}
+
+// The collectives of one step (dense all-reduce + the row all-gathers) go out as ONE NCCL group: one fused launch
+// instead of five back-to-back kernels.
+int comm_group_begin(Model* m) {
+  if (!m->comm) { m->err = "communicator not initialised"; return CFFM_ERR_COMM; }
+  ncclResult_t r = g_nccl.GroupStart();
+  if (r != ncclSuccess) { m->err = std::string("ncclGroupStart: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
+  return CFFM_OK;
+}
+int comm_group_end(Model* m) {
+  ncclResult_t r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) { m->err = std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
   return CFFM_OK;
 }
 

@@ -164,6 +164,8 @@ int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows);
 
 int comm_allreduce_f32(Model* m, float* buf, int64_t n, cudaStream_t s);
 int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s);
+int comm_group_begin(Model* m);
+int comm_group_end(Model* m);
 void comm_destroy(Model* m);
 
 // Brackets one launch with CUDA events on its stream when profiling is enabled.
