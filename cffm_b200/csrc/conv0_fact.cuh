@@ -51,7 +51,7 @@ struct Fwd0FactParams {
   const float* bias;
   bf16* Xout;           // X1 [B][16][16][Pp]
   float* t1; int t1_dim, sp_off;
-  int B, F, P, Pp, KA, nblk, Q16, dbg;
+  int B, F, P, Pp, KA, nblk, Q16;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
               const uint32_t d1 = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                if (k < ksteps && !(prm.dbg & 8)) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
+                if (k < ksteps) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
               umma_commit(&ctl->empty_b[u]);
               umma_commit(&ctl->z_full[zb]);
             }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
               const uint32_t za = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                if (k < ksteps && !(prm.dbg & 4)) umma_bf16_ts(d2, za + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
+                if (k < ksteps) umma_bf16_ts(d2, za + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
               umma_commit(&ctl->z_empty[zb]);        // the Z buffer (fp32 and its bf16 overlay) is free again
               umma_commit(&ctl->d2_full[u & 1]);
             }
@@ -223,7 +223,6 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
         mbar_wait(&ctl->z_full[zb], zph);
         tc_fence_after();
         float v[F0_KA_MAX / 16][16];
-        if (!(prm.dbg & 2)) {
 #pragma unroll
         for (int c = 0; c < F0_KA_MAX / 16; ++c)
           if (c * 16 < KA) tmem_ld16(zaddr + (uint32_t)(c * 16), v[c]);
@@ -237,7 +236,6 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             tmem_st8(zaddr + (uint32_t)(c * 8), pk);
           }
         tmem_st_wait();
-        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->zb_full[zb]);
@@ -294,7 +292,6 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->d2_empty[qq & 1]);
           const float bq = sbias[q0 + qq];
-          if (!(prm.dbg & 1))
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
             const float x = phi_f<ACT>((hi ? up[w] : lo[w]) + bq);
@@ -302,7 +299,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
           }
         }
-        if (prm.tma_store && !(prm.dbg & 17)) {
+        if (prm.tma_store) {
           // 32 rows x 8 w x 16 channels of this warp -> staging tile -> one TMA store (rows beyond the batch are
           // clipped by the tensor map); the copy engine does the scattered 32-byte writes, not the LSU
           if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
@@ -316,7 +313,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
-        } else if (b < prm.B && !(prm.dbg & 17)) {
+        } else if (b < prm.B) {
           bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {

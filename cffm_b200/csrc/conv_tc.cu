@@ -903,7 +903,6 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
-  { const char* e = getenv("CFFM_F0_DBG"); p.dbg = e ? atoi(e) : 0; }
   static bool attr_done = false;
   if (!attr_done) {
     CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_fwd0_fact<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F0_SMEM));
