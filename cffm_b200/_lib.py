@@ -25,7 +25,7 @@ ABI_VERSION = 1
 ACTIVATIONS = {"relu": 0, "elu": 1, "selu": 2, "prelu": 3, "gelu": 4}
 LOSSES = {"square_loss": 0, "log_loss": 1, "mse": 2, "mae": 3, "hybrid": 4}
 OPTIMIZERS = {"AdagradOptimizer": 0, "GradientDescentOptimizer": 1, "MomentumOptimizer": 2, "AdamOptimizer": 3}
-PRECISIONS = {"fp32": 0, "bf16": 1}
+PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 
 
 class CffmError(RuntimeError):
@@ -65,6 +65,7 @@ def build(force=False, verbose=False):
     stamp = os.path.join(BUILD_DIR, "cffm.digest")
     digest = _source_digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
+        _record_build(False, digest, [])
         return LIB_PATH
     nvcc = _nvcc()
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
@@ -88,7 +89,26 @@ def build(force=False, verbose=False):
     os.replace(tmp, LIB_PATH)
     with open(stamp, "w") as fh:
         fh.write(digest)
+    _record_build(True, digest, CU_SOURCES + CPP_SOURCES)
     return LIB_PATH
+
+
+LAST_BUILD = None
+
+
+def _record_build(nvcc_ran, digest, compiled):
+    """Makes the rebuild observable: ``LAST_BUILD`` (and build/build_record.json) say whether this call ran nvcc
+    or found the in-tree library up to date with the sources (same digest)."""
+    global LAST_BUILD
+    import json
+    import time
+    LAST_BUILD = {"nvcc_ran": bool(nvcc_ran), "compiled": list(compiled), "source_digest": digest, "library": LIB_PATH,
+                  "arch": ARCH_FLAGS[1], "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
+    try:
+        with open(os.path.join(BUILD_DIR, "build_record.json"), "w") as fh:
+            json.dump(LAST_BUILD, fh, indent=1)
+    except OSError:
+        pass
 
 
 _lib = None
@@ -109,6 +129,9 @@ def _declare(lib):
         "cffm_get_accum": (C.c_int, [vp, C.c_char_p, vp, i64]),
         "cffm_set_accum": (C.c_int, [vp, C.c_char_p, vp, i64]),
         "cffm_init_params": (C.c_int, [vp, C.c_uint64]),
+        "cffm_get_opt_step": (C.c_int, [vp, P(i64)]),
+        "cffm_set_opt_step": (C.c_int, [vp, i64]),
+        "cffm_uses_graph": (C.c_int, [vp]),
         "cffm_forward_dev": (C.c_int, [vp, vp, i64, vp, vp]),
         "cffm_forward_host": (C.c_int, [vp, vp, i64, vp]),
         "cffm_train_step_dev": (C.c_int, [vp, vp, vp, i64, vp, vp]),

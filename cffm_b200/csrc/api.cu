@@ -84,6 +84,8 @@ extern "C" int cffm_synchronize(cffm_handle* h) {
   return CFFM_OK;
 }
 
+extern "C" int cffm_uses_graph(const cffm_handle* h) { return h && h->m.use_graph ? 1 : 0; }
+
 extern "C" int64_t cffm_launch_count(const cffm_handle* h) { return h ? h->m.launches : 0; }
 
 // ---- per-kernel timing ------------------------------------------------------------------------
@@ -184,6 +186,30 @@ extern "C" int cffm_set_param(cffm_handle* h, const char* n, const float* s, int
 extern "C" int cffm_get_accum(cffm_handle* h, const char* n, float* d, int64_t k) { return param_copy(h, n, d, k, true, true); }
 extern "C" int cffm_set_accum(cffm_handle* h, const char* n, const float* s, int64_t k) { return param_copy(h, n, const_cast<float*>(s), k, true, false); }
 
+// Adam's step counter lives in scalars[5] (a float: exact up to 2^24 steps), advanced by k_adam_tick
+extern "C" int cffm_get_opt_step(cffm_handle* h, int64_t* step) {
+  if (!h || !step) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  *step = 0;
+  if (m->cfg.optimizer != CFFM_OPT_ADAM) return CFFM_OK;
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  float t = 0.f;
+  CFFM_CUDA_OK(m, cudaMemcpy(&t, m->scalars + 5, sizeof(float), cudaMemcpyDeviceToHost));
+  *step = (int64_t)t;
+  return CFFM_OK;
+}
+extern "C" int cffm_set_opt_step(cffm_handle* h, int64_t step) {
+  if (!h || step < 0 || step >= (1 << 24)) return CFFM_ERR_INVALID;
+  Model* m = &h->m;
+  if (m->cfg.optimizer != CFFM_OPT_ADAM) return CFFM_OK;
+  CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
+  const float t = (float)step;
+  CFFM_CUDA_OK(m, cudaMemcpy(m->scalars + 5, &t, sizeof(float), cudaMemcpyHostToDevice));
+  return CFFM_OK;
+}
+
 extern "C" int cffm_init_params(cffm_handle* h, uint64_t seed) {
   if (!h) return CFFM_ERR_INVALID;
   CFFM_CUDA_OK(&h->m, cudaSetDevice(h->m.device));
@@ -222,9 +248,12 @@ extern "C" int cffm_forward_host(cffm_handle* h, const int32_t* ids_host, int64_
   if (!h || !ids_host || !out_host || N < 1) return CFFM_ERR_INVALID;
   Model* m = &h->m;
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
+  // the pinned staging slot may still feed the H2D copy of a pipelined training step
+  if (m->pending) { m->err = "cffm_train_flush the pipelined steps first"; return CFFM_ERR_INVALID; }
   const int F = m->F;
   for (int64_t o = 0; o < N; o += m->max_batch) {  // ordered blocks, last one partial (CFFM.py:617-629)
     const int64_t B = std::min<int64_t>(m->max_batch, N - o);
+    CFFM_CUDA_OK(m, cudaEventSynchronize(m->slot_done[0]));
     memcpy(m->h_ids[0], ids_host + o * F, sizeof(int32_t) * B * F);
     CFFM_CUDA_OK(m, cudaMemcpyAsync(m->ids_buf, m->h_ids[0], sizeof(int32_t) * B * F, cudaMemcpyHostToDevice, m->stream));
     int r = run_forward(m, m->ids_buf, nullptr, B, m->stream); if (r != CFFM_OK) return r;
@@ -656,7 +685,7 @@ extern "C" int cffm_debug_fetch(cffm_handle* h, const char* what, float* host_ds
     if (l < 0 || l >= m->n_live) { m->err = "no such conv layer"; return CFFM_ERR_INVALID; }
     const int64_t H = m->Ko >> (l + 1);
     n = B * H * H * P;
-    if (m->cfg.precision == CFFM_PREC_BF16) {  // bf16 mode stores X_{l+1} = phi(Y_l) (and dY_l) padded, in bf16
+    if (tc_path(m)) {  // bf16 mode stores X_{l+1} = phi(Y_l) (and dY_l) padded, in bf16
       if (n_out) *n_out = n;
       if (!host_dst || cap <= 0) return CFFM_OK;
       float* tmp = nullptr;

@@ -457,7 +457,7 @@ static TrainPlan make_plan(const Model* m) {
   pl.off_rows = take(m->n_small, pl.Cb);
   pl.off_Wd = m->cfg.inner_conv ? take(P * m->Ki, pl.Cb) : 0;
   pl.off_attW = m->cfg.linear_att ? take(F * F, pl.Cb) : 0;
-  for (int l = 0; l < (m->cfg.precision == CFFM_PREC_BF16 ? 0 : m->n_live); ++l) {
+  for (int l = 0; l < (tc_path(m) ? 0 : m->n_live); ++l) {
     const int64_t Ho = m->Ko >> (l + 1);
     const int64_t rows = B * Ho * Ho;
     const int tiles = ceil_div(4 * P, GBM) * ceil_div(P, GBN);
@@ -478,7 +478,7 @@ int model_alloc_train(Model* m) {
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   TRY(dmalloc(m, &m->gout, B));
   if (m->cfg.outer_conv) {
-    if (m->cfg.precision == CFFM_PREC_BF16) {
+    if (tc_path(m)) {
       TRY(tc_alloc(m, true));
     } else {
       for (int l = 0; l < m->n_live; ++l) {
@@ -504,7 +504,7 @@ int model_alloc_train(Model* m) {
   add(pl.off_rows, m->aux_off + m->t1_dim + 4, m->n_small, pl.Cb);
   if (m->cfg.inner_conv) add(pl.off_Wd, L.din_k, (int64_t)m->P * m->Ki, pl.Cb);
   if (m->cfg.linear_att) add(pl.off_attW, L.att_W, F * F, pl.Cb);
-  for (int l = 0; l < (m->cfg.precision == CFFM_PREC_BF16 ? 0 : m->n_live); ++l) {  // bf16: conv_tc.cu writes these
+  for (int l = 0; l < (tc_path(m) ? 0 : m->n_live); ++l) {  // bf16: conv_tc.cu writes these
     add(pl.off_wg[l], L.conv_w[l], 4ll * m->P * m->P, pl.nsplit[l]);
     add(pl.off_bg[l], L.conv_b[l], m->P, pl.Cl[l]);
   }
@@ -581,12 +581,12 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     // offsets of the pooling levels inside t1
     int lvl_off[kMaxConv + 1]; lvl_off[0] = 0;
     for (int l = 0; l < m->conv_depth; ++l) lvl_off[l + 1] = lvl_off[l] + (K >> l);
-    if (m->cfg.precision == CFFM_PREC_BF16) {
+    if (tc_path(m)) {
       int r = tc_conv_backward(m, B, s);
       if (r != CFFM_OK) return r;
     }
     // ---- top of the conv stack ----
-    if (m->cfg.precision != CFFM_PREC_BF16) {
+    if (!tc_path(m)) {
       const int l = m->n_live - 1;
       const int H = K >> (l + 1);
       const int64_t total = (int64_t)B * H * H * P;
@@ -595,7 +595,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
           m->Y[l], m->gout, m->v_head + lvl_off[l + 1], H, P, total, m->dY[l]));
       m->launches++;
     }
-    for (int l = (m->cfg.precision == CFFM_PREC_BF16 ? -1 : m->n_live - 1); l >= 0; --l) {
+    for (int l = (tc_path(m) ? -1 : m->n_live - 1); l >= 0; --l) {
       const int Hin = K >> l, Ho = Hin >> 1;
       const int rows = B * Ho * Ho;
       launch_colsum(m, m->dY[l], rows, P, P, nullptr, part + pl.off_bg[l], pl.Cl[l], s);
@@ -685,12 +685,19 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   int64_t n_upd = (int64_t)B * F;
   if (m->world > 1) {
     CFFM_PROF(m, "dp_allreduce_allgather", s);
+    // the group is closed on every exit path (an open NCCL group inside a stream capture poisons the communicator)
+    struct GroupGuard {
+      Model* m; bool open;
+      ~GroupGuard() { if (open) comm_group_end(m); }
+    } guard{m, false};
     int r = comm_group_begin(m); if (r != CFFM_OK) return r;
-    r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
-    r = comm_allgather(m, ids, m->all_ids, sizeof(int32_t) * n_upd, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
+    guard.open = true;
+    r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) return r;
+    r = comm_allgather(m, ids, m->all_ids, sizeof(int32_t) * n_upd, s); if (r != CFFM_OK) return r;
     if (m->cfg.inner_conv) { r = comm_allgather(m, gi, m->all_g_inner, sizeof(float) * n_upd * m->Ki, s); if (r != CFFM_OK) return r; }
     if (m->cfg.outer_conv) { r = comm_allgather(m, go, m->all_g_outer, sizeof(float) * n_upd * m->Ko, s); if (r != CFFM_OK) return r; }
-    r = comm_allgather(m, gbr, m->all_g_bias, sizeof(float) * n_upd, s); if (r != CFFM_OK) { comm_group_end(m); return r; }
+    r = comm_allgather(m, gbr, m->all_g_bias, sizeof(float) * n_upd, s); if (r != CFFM_OK) return r;
+    guard.open = false;
     r = comm_group_end(m); if (r != CFFM_OK) return r;
     upd_ids = m->all_ids; gi = m->all_g_inner; go = m->all_g_outer; gbr = m->all_g_bias;
     n_upd *= m->world;

@@ -73,6 +73,26 @@ __device__ __forceinline__ float warp_max(float v) {
     default: { constexpr int ACT = CFFM_ACT_GELU; __VA_ARGS__; } break;              \
   }
 
+// The conv stack only sees the activation through phi = activation o relu, and relu / elu / prelu are
+// the identity on relu's range: three distinct instantiations instead of five.
+#define CFFM_DISPATCH_PHI(act, ...)                                         \
+  switch (act) {                                                            \
+    case CFFM_ACT_SELU: { constexpr int ACT = CFFM_ACT_SELU; __VA_ARGS__; } break;   \
+    case CFFM_ACT_GELU: { constexpr int ACT = CFFM_ACT_GELU; __VA_ARGS__; } break;   \
+    default: { constexpr int ACT = CFFM_ACT_RELU; __VA_ARGS__; } break;              \
+  }
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute is per device (context): a "done" flag has to be kept per device ordinal, or a second
+// handle on another GPU of the same process launches without its shared-memory opt-in.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool& operator()() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    return done[d];
+  }
+};
 
 }  // namespace cffm

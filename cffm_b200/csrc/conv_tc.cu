@@ -51,10 +51,31 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 template <int ACT>
 __device__ __forceinline__ float phi_scale() { return ACT == CFFM_ACT_SELU ? kSeluScale : 1.f; }
 
+// ---- split-bf16 ("bf16x3", CFFM_PREC_BF16X3): fp32-class accuracy on the bf16 tensor cores -------------------
+// Every operand is kept as hi + lo with hi = bf16(x), lo = bf16(x - hi) (|x - hi - lo| <= 2^-18 |x|) and a product
+// a*b is taken as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (the dropped lo*lo term is 2^-18 relative as well), all three
+// accumulated in the same fp32 TMEM accumulator.  In the pipeline this is a GEMM with a three times longer
+// reduction axis, [A_hi | A_lo | A_hi] . [B_hi ; B_hi ; B_lo]: reduction chunk kc of a unit is chunk kc / 3 of
+// the plain operands in part kc % 3, so only the loaders (which tensor map / which half to synthesise) and the
+// epilogues (which write hi and lo) know about it; k_tc itself is unchanged.
+__device__ __forceinline__ uint32_t pack2_lo(float lo, float hi) {   // the lo halves of two values
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  const float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo - hf.x, hi - hf.y);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+struct SplitK {
+  int nparts = 1;                 // 1: plain bf16, 3: split
+  __device__ __forceinline__ int part(int kc) const { return nparts == 1 ? 0 : kc % 3; }
+  __device__ __forceinline__ int base(int kc) const { return nparts == 1 ? kc : kc / 3; }
+  __device__ __forceinline__ bool a_lo(int kc) const { return part(kc) == 1; }
+  __device__ __forceinline__ bool b_lo(int kc) const { return part(kc) == 2; }
+};
+
 // =================================================================================================
 // Forward: Y_l = conv(X_l) + b_l ; X_{l+1} = phi(Y_l) (bf16) ; sum_pooling[l+1][b,h] = sum_{w,q} X_{l+1}
 // =================================================================================================
-template <int ACT, bool L0>
+template <int ACT, bool L0, bool SPLIT = false>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
   static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = L0 ? 8 : 4;
@@ -62,8 +83,9 @@ struct ConvFwdTC : KMajorA, KMajorB {
   // the kernel was bound by shared-memory bandwidth (STS of the slab + UMMA reads of A and B + LDS of the rows)
   // ... and every slab feeds two N tiles (kBPair): the producers, not the tensor pipe, bounded the kernel
   static constexpr bool kATmem = L0, kSynthAlternate = L0, kBPair = L0, kEpiPrefetch = false;
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapA2, mapB2;   // *2: the lo halves (split mode)
   Geom g;
+  SplitK sk; bf16* Xout_lo;
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
   float* pool_part;         // l >= 1, tiles_n > 1: pooled sums per N tile [tiles_n][B*Ho], added up by k_pool_parts
   const float* rows; const int* pair_i; const int* pair_j;
@@ -86,16 +108,22 @@ struct ConvFwdTC : KMajorA, KMajorB {
     const int u = cta + it * ncta;
     return {u / g.tiles_n, u % g.tiles_n, 0};
   }
-  __device__ int k_chunks(Unit) const { return 4 * g.Pp / BK; }
+  __device__ int k_chunks(Unit) const { return (4 * g.Pp / BK) * sk.nparts; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(L0 ? 2 * g.BN * BK * 2 : A_STAGE_BYTES + g.BN * BK * 2); }
-  __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void prefetch() const {
+    if (!L0) prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    if (sk.nparts > 1) { if (!L0) prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+  }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
     const int m0 = un.m_tile * BM;
     const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
-    const int k0 = kc * BK, dh = k0 / (2 * g.Pp), c0 = k0 - dh * 2 * g.Pp;
-    tma_load_5d(s, &mapA, bar, c0, 0, dh, h0, b0);
+    const int k0 = sk.base(kc) * BK, dh = k0 / (2 * g.Pp), c0 = k0 - dh * 2 * g.Pp;
+    tma_load_5d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, c0, 0, dh, h0, b0);
   }
-  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    tma_load_2d(s, sk.b_lo(kc) ? &mapB2 : &mapB, bar, sk.base(kc) * BK, un.n_tile * g.BN);
+  }
   // ---- layer 0: stage the sample's outer rows, then build 128 x 64 slabs of the cube ----
   // Shared scratch of the producers: rows o[F+1][K] (row F = zeros, the target of padded pairs) and a
   // table with one entry per pair of every stage: byte offsets of rows i and j (lo / hi 16 bits).
@@ -113,7 +141,9 @@ struct ConvFwdTC : KMajorA, KMajorB {
       tab[e] = e < g.P ? ((uint32_t)(pair_i[e] * g.K * 4) | ((uint32_t)(pair_j[e] * g.K * 4) << 16)) : (zero_row | (zero_row << 16));
   }
   // 8 pairs x 4 taps = 32 bf16 = 16 packed columns of this thread's row (columns half*16 .. +15 of the stage)
-  __device__ void synth_regs(uint32_t (&pk)[16], Unit un, int kc, int t256, const uint8_t* ex) const {
+  __device__ void synth_regs(uint32_t (&pk)[16], Unit un, int kc_in, int t256, const uint8_t* ex) const {
+    const int kc = sk.base(kc_in);
+    const bool lo_part = sk.a_lo(kc_in);
     const uint8_t* o = ex;
     const uint32_t* tab = reinterpret_cast<const uint32_t*>(ex + (g.F + 1) * g.K * 4);
     const int t = t256 & 127, half = t256 >> 7;
@@ -131,8 +161,13 @@ struct ConvFwdTC : KMajorA, KMajorB {
       const uint32_t en = ent[pr];
       if ((en & 0xFFFFu) != cur_i) { cur_i = en & 0xFFFFu; oi = *reinterpret_cast<const float2*>(oh + cur_i); }  // uniform: pairs run i-major
       const float2 oj = *reinterpret_cast<const float2*>(ow + (en >> 16));
-      pk[pr * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
-      pk[pr * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
+      if (SPLIT && lo_part) {   // warp-uniform
+        pk[pr * 2 + 0] = pack2_lo(oi.x * oj.x, oi.x * oj.y);
+        pk[pr * 2 + 1] = pack2_lo(oi.y * oj.x, oi.y * oj.y);
+      } else {
+        pk[pr * 2 + 0] = pack2(oi.x * oj.x, oi.x * oj.y);
+        pk[pr * 2 + 1] = pack2(oi.y * oj.x, oi.y * oj.y);
+      }
     }
   }
   __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex, SynthState&) const {
@@ -169,6 +204,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
       const int n0 = un.n_tile * p.g.BN + c0;
       if (L0 && n0 >= p.g.Pp) return;     // N tiles may overhang the padded channel count (zero weights)
       uint32_t pk[16];
+      uint32_t pl[SPLIT ? 16 : 1];
       float bv[32];
       if (L0) {
 #pragma unroll
@@ -187,11 +223,17 @@ struct ConvFwdTC : KMajorA, KMajorB {
         const float x0 = phi_f<ACT>(y0), x1 = phi_f<ACT>(y1);
         rowsum += x0 + x1;
         pk[j >> 1] = pack2(x0, x1);
+        if constexpr (SPLIT) pl[j >> 1] = pack2_lo(x0, x1);
       }
       if (m < p.g.M) {
         uint4* dst = reinterpret_cast<uint4*>(p.Xout + (int64_t)m * p.g.Pp + n0);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        if constexpr (SPLIT) {
+          uint4* dl = reinterpret_cast<uint4*>(p.Xout_lo + (int64_t)m * p.g.Pp + n0);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) dl[q4] = make_uint4(pl[4 * q4], pl[4 * q4 + 1], pl[4 * q4 + 2], pl[4 * q4 + 3]);
+        }
       }
     }
     __device__ void end(Unit un) {
@@ -231,25 +273,33 @@ __global__ void k_pool_parts(const float* __restrict__ part, int tiles_n, int B,
 //   dX_l[b,2h+dh,2w+dw,p] = sum_q dY_l[m,q] W_l[(dh,dw,p),q] + g_b v[sp_off + 2h+dh]
 //   dY_{l-1} = dX_l * phi'(Y_{l-1}); phi' follows from the sign of X_l = phi(Y_{l-1})
 // =================================================================================================
-template <int ACT>
+template <int ACT, bool SPLIT = false>
 struct ConvDgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   // eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks); scratch = their staging tiles
   static constexpr int kStages = 4, kExtraBytes = 8 * 32 * 80, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
   static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = true;
-  CUtensorMap mapA, mapB;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN)
+  CUtensorMap mapA, mapB, mapA2, mapB2;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN); *2: lo halves
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
+  SplitK sk; bf16* dYprev_lo;
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
   __device__ int bn() const { return g.BN; }
   __device__ int n_units() const { return ((g.M + BM - 1) / BM) * g.tiles_n; }
   __device__ int n_iters(int cta, int ncta) const { const int n = n_units(); return cta < n ? (n - cta + ncta - 1) / ncta : 0; }
   __device__ Unit unit(int cta, int ncta, int it) const { const int u = cta + it * ncta; return {u / g.tiles_n, u % g.tiles_n, 0}; }
-  __device__ int k_chunks(Unit) const { return g.Pp / BK; }
+  __device__ int k_chunks(Unit) const { return (g.Pp / BK) * sk.nparts; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + g.BN * BK * 2); }
-  __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
-  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
-  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  __device__ void prefetch() const {
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+    if (sk.nparts > 1) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+  }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    tma_load_2d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, sk.base(kc) * BK, un.m_tile * BM);
+  }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    tma_load_2d(s, sk.b_lo(kc) ? &mapB2 : &mapB, bar, sk.base(kc) * BK, un.n_tile * g.BN);
+  }
   struct SynthState {};
   __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
   __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
@@ -300,6 +350,14 @@ struct ConvDgradTC : KMajorA, KMajorB {
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 2) o[j >> 1] = pack2((v[j] + dsp) * phi_scale<ACT>(), (v[j + 1] + dsp) * phi_scale<ACT>());
+      stage_store(ci, c0, o, p.dYprev);
+      if constexpr (SPLIT) {                          // split mode: the lo halves take the same route
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) o[j >> 1] = pack2_lo((v[j] + dsp) * phi_scale<ACT>(), (v[j + 1] + dsp) * phi_scale<ACT>());
+        stage_store(ci, c0, o, p.dYprev_lo);
+      }
+    }
+    __device__ __forceinline__ void stage_store(int ci, int c0, const uint32_t (&o)[16], bf16* dst) {
       __syncwarp();                                   // the previous chunk has been read out of the staging tile
       uint4* mine = reinterpret_cast<uint4*>(stg + lane * STG);
 #pragma unroll
@@ -310,7 +368,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
         uint4 d = *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * STG + (lane & 3) * 16);
         const uint4 x = mk[ci][i];
         d.x &= keep_bits(x.x); d.y &= keep_bits(x.y); d.z &= keep_bits(x.z); d.w &= keep_bits(x.w);
-        if (cok[i]) *reinterpret_cast<uint4*>(p.dYprev + cbase[i] + c0) = d;
+        if (cok[i]) *reinterpret_cast<uint4*>(dst + cbase[i] + c0) = d;
       }
     }
     __device__ void end(Unit) {}
@@ -330,8 +388,9 @@ struct Conv0DgradTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = false;
   static constexpr int kStages = 3, kExtraBytes = 72 * 1024, kATiles = 1, kAccBufs = 2, kEpiWarps = 8;
   static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
-  CUtensorMap mapA, mapB;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN)
+  CUtensorMap mapA, mapB, mapA2, mapB2;   // A: dY_0 dims (Pp, M) box (64,128); B: Wd0 dims (Pp, 4Pp) box (64, BN); *2: lo halves
   Geom g;                   // Ho = 16: 256 rows per sample
+  SplitK sk;
   const float* rows; const float* gout; const float* v_head; const int* pair_i; const int* pair_j; float* g_rows;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
   __device__ int bn() const { return g.BN; }
@@ -342,11 +401,18 @@ struct Conv0DgradTC : KMajorA, KMajorB {
     const int b = cta + (it / ps) * ncta, r = it % ps;
     return {b * 2 + r / g.tiles_n, r % g.tiles_n, r};  // z = position inside the sample's unit sequence
   }
-  __device__ int k_chunks(Unit) const { return g.Pp / BK; }
+  __device__ int k_chunks(Unit) const { return (g.Pp / BK) * sk.nparts; }
   __device__ uint32_t tx_bytes() const { return (uint32_t)(A_STAGE_BYTES + g.BN * BK * 2); }
-  __device__ void prefetch() const { prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
-  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapA, bar, kc * BK, un.m_tile * BM); }
-  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const { tma_load_2d(s, &mapB, bar, kc * BK, un.n_tile * g.BN); }
+  __device__ void prefetch() const {
+    prefetch_tmap(&mapA); prefetch_tmap(&mapB);
+    if (sk.nparts > 1) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+  }
+  __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    tma_load_2d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, sk.base(kc) * BK, un.m_tile * BM);
+  }
+  __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
+    tma_load_2d(s, sk.b_lo(kc) ? &mapB2 : &mapB, bar, sk.base(kc) * BK, un.n_tile * g.BN);
+  }
   struct SynthState {};
   __device__ void synth_begin(Unit, uint8_t*, int, SynthState&) const {}
   __device__ void synth_a(uint8_t*, Unit, int, int, const uint8_t*, SynthState&) const {}
@@ -511,7 +577,7 @@ struct Conv0DgradTC : KMajorA, KMajorB {
 // B (= dY_l) is MN-major via TMA; A is MN-major via the im2col TMA box (l >= 1) or synthesised
 // K-major by the producer warps (layer 0: the cube).
 // =================================================================================================
-template <int ACT, bool L0>
+template <int ACT, bool L0, bool SPLIT = false>
 struct ConvWgradTC : KMajorA, MNMajorB {
   static constexpr bool kSynthA = L0;
   // layer 0: two 128-row A tiles (256 cube channels) share every dY stage -> half the L2 traffic of B;
@@ -520,8 +586,9 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   static constexpr bool kATmem = false, kSynthAlternate = false, kBPair = false, kEpiPrefetch = false;
   static constexpr int kStages = L0 ? 3 : 4, kExtraBytes = L0 ? 24 * 1024 : 0;
   static constexpr int kRows = kATiles * BM;   // cube channels (rows of dW) per unit
-  CUtensorMap mapA, mapB;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64)
+  CUtensorMap mapA, mapB, mapA2, mapB2;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64); *2: lo halves
   Geom g;                   // BN divides Pp, multiple of 64
+  SplitK sk;
   int chunks_total, chunks_per_split, n_split;
   float* partial;
   const float* rows; const int* pair_i; const int* pair_j;
@@ -543,23 +610,29 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   __device__ int k_chunks(Unit un) const {
     const int c0 = un.z * chunks_per_split;
     const int c1 = min(chunks_total, c0 + chunks_per_split);
-    return c1 - c0;
+    return (c1 - c0) * sk.nparts;
   }
   __device__ uint32_t tx_bytes() const { return (uint32_t)((L0 ? 0 : A_STAGE_BYTES) + g.BN * BK * 2); }
-  __device__ void prefetch() const { if (!L0) prefetch_tmap(&mapA); prefetch_tmap(&mapB); }
+  __device__ void prefetch() const {
+    if (!L0) prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    if (sk.nparts > 1) { if (!L0) prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+  }
   __device__ void load_a(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
-    const int m0 = (un.z * chunks_per_split + kc) * BK;   // first of the 64 positions of this stage
+    const int m0 = (un.z * chunks_per_split + sk.base(kc)) * BK;   // first of the 64 positions of this stage
     const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
+    const CUtensorMap* map = sk.a_lo(kc) ? &mapA2 : &mapA;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int kk0 = (un.m_tile * (kRows / 64) + i) * 64;
       const int dh = kk0 / (2 * g.Pp), c0 = kk0 - dh * 2 * g.Pp;
-      tma_load_5d(s + i * 8192, &mapA, bar, c0, 0, dh, h0, b0);
+      tma_load_5d(s + i * 8192, map, bar, c0, 0, dh, h0, b0);
     }
   }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
-    const int m0 = (un.z * chunks_per_split + kc) * BK;
-    for (int i = 0; i < g.BN / 64; ++i) tma_load_2d(s + i * 8192, &mapB, bar, un.n_tile * g.BN + i * 64, m0);
+    const int m0 = (un.z * chunks_per_split + sk.base(kc)) * BK;
+    const CUtensorMap* map = sk.b_lo(kc) ? &mapB2 : &mapB;
+    for (int i = 0; i < g.BN / 64; ++i) tma_load_2d(s + i * 8192, map, bar, un.n_tile * g.BN + i * 64, m0);
   }
   // ---- layer 0: rows of the A stage are cube channels k = p*4 + dh*2 + dw, columns 64 positions ----
   // A thread owns one channel row (pair, dh, dw) for the whole unit.  Its 16 values o_j[2w+dw] only
@@ -578,8 +651,10 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     st.oi_off = (live ? pair_i[pr] : g.F) * KS + dh;
     st.oj_off = (live ? pair_j[pr] : g.F) * KS + dw;
   }
-  __device__ void synth_a(uint8_t* sA, Unit un, int kc, int t256, const uint8_t* ex_c, SynthState& st) const {
+  __device__ void synth_a(uint8_t* sA, Unit un, int kc_in, int t256, const uint8_t* ex_c, SynthState& st) const {
     uint8_t* ex = const_cast<uint8_t*>(ex_c);
+    const int kc = sk.base(kc_in);
+    const bool lo_part = sk.a_lo(kc_in);
     const int t = t256 & 127, tile = t256 >> 7;          // row inside its 128-row tile; which of the two A tiles
     const int KS = g.K + 4;
     float* o = reinterpret_cast<float*>(ex);
@@ -609,7 +684,9 @@ struct ConvWgradTC : KMajorA, MNMajorB {
       const float a = oi[2 * (c >> 1)];
       uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pk[e] = pack2(a * st.oj[(c & 1) * 8 + 2 * e], a * st.oj[(c & 1) * 8 + 2 * e + 1]);
+      for (int e = 0; e < 4; ++e)
+        pk[e] = (SPLIT && lo_part) ? pack2_lo(a * st.oj[(c & 1) * 8 + 2 * e], a * st.oj[(c & 1) * 8 + 2 * e + 1])
+                        : pack2(a * st.oj[(c & 1) * 8 + 2 * e], a * st.oj[(c & 1) * 8 + 2 * e + 1]);
       *reinterpret_cast<uint4*>(sT + sw128_offset(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
@@ -635,7 +712,8 @@ struct ConvWgradTC : KMajorA, MNMajorB {
 // bf16 operand copies of the fp32 master filters W_l[(tap,p), q] (HWIO, CFFM.py:376-377):
 //   Wt[q][kk] (forward B operand) and Wd[kk][q] (data-gradient B operand), zero padded, with
 //   kk = tap*Pp + p for l >= 1 and kk = p*4 + tap for layer 0 (the order the cube is synthesised in).
-__global__ void k_prep_weights(const float* __restrict__ W, int P, int Pp, int l0, bf16* __restrict__ Wt, bf16* __restrict__ Wd) {
+__global__ void k_prep_weights(const float* __restrict__ W, int P, int Pp, int l0, bf16* __restrict__ Wt, bf16* __restrict__ Wd,
+                               bf16* __restrict__ Wt_lo, bf16* __restrict__ Wd_lo) {
   const int64_t total = (int64_t)4 * Pp * Pp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int kk = (int)(e / Pp), q = (int)(e - (int64_t)kk * Pp);
@@ -645,6 +723,11 @@ __global__ void k_prep_weights(const float* __restrict__ W, int P, int Pp, int l
     const bf16 b = __float2bfloat16_rn(v);
     Wd[e] = b;
     Wt[(int64_t)q * 4 * Pp + kk] = b;
+    if (Wt_lo) {   // split mode: lo = bf16(v - hi)
+      const bf16 bl = __float2bfloat16_rn(v - __bfloat162float(b));
+      Wd_lo[e] = bl;
+      Wt_lo[(int64_t)q * 4 * Pp + kk] = bl;
+    }
   }
 }
 
@@ -664,7 +747,8 @@ __global__ void k_wgrad_reduce(const float* __restrict__ partial, int n_split, i
 // d b_l[q] = sum_m dY_l[m, q]: chunk partials over the rows, then the chunks in order.
 // A thread owns 8 adjacent channels (one 16-byte load per row) and every R-th row of the chunk; the R
 // row lanes are combined through shared memory in a fixed order.  blockDim = (Pp/8) * R.
-__global__ void k_colsum_bf16(const bf16* __restrict__ X, int64_t rows, int Pp, int n, float* __restrict__ partial, int C) {
+__global__ void k_colsum_bf16(const bf16* __restrict__ X, const bf16* __restrict__ Xlo, int64_t rows, int Pp, int n,
+                              float* __restrict__ partial, int C) {
   extern __shared__ float red[];               // [R][Pp]
   const int CG = Pp >> 3;
   const int R = blockDim.x / CG;
@@ -684,6 +768,15 @@ __global__ void k_colsum_bf16(const bf16* __restrict__ X, int64_t rows, int Pp, 
       for (int j = 0; j < 4; ++j) {
         acc[2 * j] += __uint_as_float(wv[j] << 16);
         acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      }
+      if (Xlo) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(Xlo + r * Pp) + cg);
+        const uint32_t uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(uv[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(uv[j] & 0xFFFF0000u);
+        }
       }
     }
 #pragma unroll
@@ -707,7 +800,7 @@ __global__ void k_sum_chunks(const float* __restrict__ partial, int n, int C, fl
 // dY of the last live layer: X_{d-1} feeds sum_pooling[d-1] only
 template <int ACT>
 __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restrict__ gout, const float* __restrict__ v_lvl,
-                              int H, int Pp, int64_t total, bf16* __restrict__ dY) {
+                              int H, int Pp, int64_t total, bf16* __restrict__ dY, bf16* __restrict__ dY_lo) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int64_t pix = e / Pp;
@@ -715,7 +808,10 @@ __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restric
   const int h = (int)(bh % H);
   const int64_t b = bh / H;
   const float m = __bfloat162float(X[e]) > 0.f ? phi_scale<ACT>() : 0.f;
-  dY[e] = __float2bfloat16_rn(gout[b] * v_lvl[h] * m);
+  const float v = gout[b] * v_lvl[h] * m;
+  const bf16 hi = __float2bfloat16_rn(v);
+  dY[e] = hi;
+  if (dY_lo) dY_lo[e] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 #include "conv0_fact.cuh"
@@ -735,6 +831,12 @@ struct TCState {
   bf16* dY[kMaxConv] = {};       // dY[l], l = 0..n_live-1
   bf16* Wt[kMaxConv] = {};       // [Pp][4Pp]
   bf16* Wd[kMaxConv] = {};       // [4Pp][Pp]
+  // split mode (CFFM_PREC_BF16X3): the lo halves of every operand tensor above
+  bool split = false;
+  bf16* Xlo[kMaxConv + 1] = {};
+  bf16* dYlo[kMaxConv] = {};
+  bf16* Wtlo[kMaxConv] = {};
+  bf16* Wdlo[kMaxConv] = {};
   float* wg_partial = nullptr;   // weight-gradient split scratch
   int64_t wg_partial_floats = 0;
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
@@ -782,16 +884,22 @@ int tc_alloc(Model* m, bool train) {
     if (!st->enc.init()) { m->err = "cuTensorMapEncodeTiled is not available"; return CFFM_ERR_CUDA; }
     st->Pp = (m->P + 63) & ~63;   // one 64-element swizzle atom is the unit of every operand box
     st->BN = pick_bn(st->Pp);
+    st->split = m->cfg.precision == CFFM_PREC_BF16X3;
     const int64_t B = m->max_batch, Pp = st->Pp;
     for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
     for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
+    if (st->split) {
+      for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->Xlo[l], B * H * H * Pp)); }
+      for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wtlo[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wdlo[l], 4 * Pp * Pp)); }
+    }
     TCTRY(tcmalloc(m, &st->pool_part, (Pp / st->BN) * B * (m->Ko >> 2)));
     const char* f0 = getenv("CFFM_FWD0");
     const char* mb = getenv("CFFM_FACT_MIN_BATCH");
     const char* mf = getenv("CFFM_FACT_MIN_FIELDS");
     if (mb) st->fact_min_batch = atoi(mb);
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
-    if (2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
+    // (split mode keeps layer 0 in the direct form: the factorised kernels round their intermediate Z / E to bf16)
+    if (!st->split && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
       st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0, n));
@@ -803,6 +911,8 @@ int tc_alloc(Model* m, bool train) {
   if (train && !st->dY[0]) {
     const int64_t B = m->max_batch, Pp = st->Pp;
     for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dY[l], B * H * H * Pp)); }
+    if (st->split)
+      for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dYlo[l], B * H * H * Pp)); }
     // split factor of the largest weight gradient decides the scratch size
     const int tiles = (4 * st->Pp / BM) * (st->Pp / st->BN);
     int max_split = (2 * 148 + tiles - 1) / tiles; if (max_split < 1) max_split = 1;
@@ -830,8 +940,11 @@ int tc_alloc(Model* m, bool train) {
 void tc_free(Model* m) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   if (!st) return;
-  for (int l = 0; l <= kMaxConv; ++l) if (st->X[l]) cudaFree(st->X[l]);
-  for (int l = 0; l < kMaxConv; ++l) { if (st->dY[l]) cudaFree(st->dY[l]); if (st->Wt[l]) cudaFree(st->Wt[l]); if (st->Wd[l]) cudaFree(st->Wd[l]); }
+  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) cudaFree(st->X[l]); if (st->Xlo[l]) cudaFree(st->Xlo[l]); }
+  for (int l = 0; l < kMaxConv; ++l) {
+    if (st->dY[l]) cudaFree(st->dY[l]); if (st->Wt[l]) cudaFree(st->Wt[l]); if (st->Wd[l]) cudaFree(st->Wd[l]);
+    if (st->dYlo[l]) cudaFree(st->dYlo[l]); if (st->Wtlo[l]) cudaFree(st->Wtlo[l]); if (st->Wdlo[l]) cudaFree(st->Wdlo[l]);
+  }
   if (st->wg_partial) cudaFree(st->wg_partial);
   if (st->bg_partial) cudaFree(st->bg_partial);
   if (st->pool_part) cudaFree(st->pool_part);
@@ -872,7 +985,8 @@ static bool mat_map(const TCState* st, CUtensorMap* map, const bf16* X, int64_t 
 
 template <class Pol>
 static int launch_tc(Model* m, const Pol& p, int units_hint, cudaStream_t s) {
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once();
   if (!attr_done) {
     static_assert(smem_bytes<Pol>() <= (size_t)SMEM_LIMIT, "policy exceeds the shared memory of an SM");
     CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_tc<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<Pol>()));
@@ -903,7 +1017,8 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once();
   if (!attr_done) {
     CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_fwd0_fact<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F0_SMEM));
     attr_done = true;
@@ -923,7 +1038,8 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   p.dY = st->dY[0]; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pterm = st->pterm0; p.g_rows = m->g_outer_rows;
   p.bpart = st->df_bpart;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once();
   if (!attr_done) {
     CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_dgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, G0_SMEM));
     attr_done = true;
@@ -946,7 +1062,8 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   for (int l = fact0 ? 1 : 0; l < m->n_live; ++l) {
     const int64_t total = 4ll * st->Pp * st->Pp;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l]);
+    k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l],
+                                          st->Wtlo[l], st->Wdlo[l]);
     m->launches++;
   }
   if (st->Wf0 && B >= st->fact_min_batch) {
@@ -957,7 +1074,7 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   return CFFM_OK;
 }
 
-template <int ACT>
+template <int ACT, bool SPLIT>
 static int conv_forward_act(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   const int K = m->Ko, Pp = st->Pp;
@@ -970,7 +1087,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     if (l == 0 && st->Wf0 && B >= st->fact_min_batch) {
       TCTRY(fwd0_fact_launch<ACT>(m, st, B, off, s));
     } else if (l == 0) {
-      ConvFwdTC<ACT, true> p;
+      ConvFwdTC<ACT, true, SPLIT> p;
       // two accumulators (one per N tile of a unit) + four A stages share the 512 TMEM columns: N <= 192.
       // An even number of N tiles covers Pp with the least overhang (weights beyond Pp: TMA zero fill).
       Geom g0 = g;
@@ -982,15 +1099,23 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
       }
       p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j; p.pool_part = nullptr;
-      memset(&p.mapA, 0, sizeof(p.mapA));
+      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[1];
+      memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g0.BN, 64));
+      if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[0], Pp, 4 * Pp, g0.BN, 64));
       TCTRY(launch_tc(m, p, m_tiles, s));
     } else {
-      ConvFwdTC<ACT, false> p;
+      ConvFwdTC<ACT, false, SPLIT> p;
       p.g = g; p.bias = m->dense_w + m->lay.conv_b[l]; p.Xout = st->X[l + 1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr; p.pool_part = st->pool_part;
+      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[l + 1];
+      memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
       TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[l], Pp, 4 * Pp, g.BN, 64));
+      if (st->split) {
+        TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, g.Hin, Pp, BM));
+        TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[l], Pp, 4 * Pp, g.BN, 64));
+      }
       TCTRY(launch_tc(m, p, m_tiles * g.tiles_n, s));
       if (g.tiles_n > 1) {
         k_pool_parts<<<(B * g.Ho + 255) / 256, 256, 0, s>>>(st->pool_part, g.tiles_n, B, g.Ho, m->t1, m->t1_dim, off);
@@ -1005,11 +1130,12 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
 int tc_conv_forward(Model* m, int B, cudaStream_t s) {
   int r = tc_prep_weights(m, B, s);
   if (r != CFFM_OK) return r;
-  CFFM_DISPATCH_ACT(m->cfg.activation, r = conv_forward_act<ACT>(m, B, s));
+  const bool split = reinterpret_cast<TCState*>(m->tcs)->split;
+  CFFM_DISPATCH_PHI(m->cfg.activation, r = split ? conv_forward_act<ACT, true>(m, B, s) : conv_forward_act<ACT, false>(m, B, s));
   return r;
 }
 
-template <int ACT>
+template <int ACT, bool SPLIT>
 static int conv_backward_act(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   const int K = m->Ko, Pp = st->Pp, P = m->P;
@@ -1021,7 +1147,8 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
     const int H = K >> (l + 1);
     const int64_t total = (int64_t)B * H * H * Pp;
     CFFM_PROF(m, "dy_top", s);
-    k_dy_top_bf16<ACT><<<ceil_div(total, 256), 256, 0, s>>>(st->X[l + 1], m->gout, m->v_head + lvl_off[l + 1], H, Pp, total, st->dY[l]);
+    k_dy_top_bf16<ACT><<<ceil_div(total, 256), 256, 0, s>>>(st->X[l + 1], m->gout, m->v_head + lvl_off[l + 1], H, Pp, total, st->dY[l],
+                                                            st->dYlo[l]);
     m->launches++;
   }
   for (int l = m->n_live - 1; l >= 0; --l) {
@@ -1032,7 +1159,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       const int C = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
       const int CG = Pp / 8;
       int R = 512 / CG; if (R < 1) R = 1; if (R > 32) R = 32;
-      k_colsum_bf16<<<C, CG * R, sizeof(float) * R * Pp, s>>>(st->dY[l], rows, Pp, P, st->bg_partial, C);
+      k_colsum_bf16<<<C, CG * R, sizeof(float) * R * Pp, s>>>(st->dY[l], st->dYlo[l], rows, Pp, P, st->bg_partial, C);
       k_sum_chunks<<<ceil_div(P, 128), 128, 0, s>>>(st->bg_partial, P, C, g + m->lay.conv_b[l]);
       m->launches += 2;
     }
@@ -1062,7 +1189,8 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         p.dY = st->dY[0]; p.part = st->wf_part;
         p.B = B; p.F = m->F; p.P = P; p.Pp = Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
         p.nsplit = std::min(W0_SPLIT_MAX, (B + 7) / 8);
-        static bool attr_done = false;
+        static PerDeviceOnce attr_once;
+        bool& attr_done = attr_once();
         if (!attr_done) {
           CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_wgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, W0_SMEM));
           attr_done = true;
@@ -1075,18 +1203,26 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         m->launches += 3;
         CFFM_CUDA_OK(m, cudaGetLastError());
       } else if (l == 0) {
-        ConvWgradTC<ACT, true> p;
+        ConvWgradTC<ACT, true, SPLIT> p;
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
         p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
-        memset(&p.mapA, 0, sizeof(p.mapA));
+        p.sk.nparts = st->split ? 3 : 1;
+        memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[0], rows, Pp, 64, 64));
+        if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[0], rows, Pp, 64, 64));
         TCTRY(launch_tc(m, p, tiles * n_split, s));
       } else {
-        ConvWgradTC<ACT, false> p;
+        ConvWgradTC<ACT, false, SPLIT> p;
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
         p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr;
+        p.sk.nparts = st->split ? 3 : 1;
+        memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, gm.Hin, Pp, 64));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[l], rows, Pp, 64, 64));
+        if (st->split) {
+          TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, gm.Hin, Pp, 64));
+          TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[l], rows, Pp, 64, 64));
+        }
         TCTRY(launch_tc(m, p, tiles * n_split, s));
       }
       if (!(l == 0 && st->wf_part && B >= st->fact_min_batch)) {
@@ -1106,14 +1242,26 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         Conv0DgradTC p;
         p.g = gd; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
         p.g_rows = m->g_outer_rows;
+        p.sk.nparts = st->split ? 3 : 1;
+        memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[0], rows, Pp, BM, 64));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wd[0], 4 * Pp, Pp, gd.BN, 64));
+        if (st->split) {
+          TC_MAP_OK(m, mat_map(st, &p.mapA2, st->dYlo[0], rows, Pp, BM, 64));
+          TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wdlo[0], 4 * Pp, Pp, gd.BN, 64));
+        }
         TCTRY(launch_tc(m, p, B, s));
       } else {
-        ConvDgradTC<ACT> p;
+        ConvDgradTC<ACT, SPLIT> p;
         p.g = gd; p.X = st->X[l]; p.dYprev = st->dY[l - 1]; p.gout = m->gout; p.v_head = m->v_head; p.sp_off = lvl_off[l];
+        p.sk.nparts = st->split ? 3 : 1; p.dYprev_lo = st->dYlo[l - 1];
+        memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[l], rows, Pp, BM, 64));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wd[l], 4 * Pp, Pp, gd.BN, 64));
+        if (st->split) {
+          TC_MAP_OK(m, mat_map(st, &p.mapA2, st->dYlo[l], rows, Pp, BM, 64));
+          TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wdlo[l], 4 * Pp, Pp, gd.BN, 64));
+        }
         TCTRY(launch_tc(m, p, ((gd.M + BM - 1) / BM) * gd.tiles_n, s));
       }
     }
@@ -1123,23 +1271,25 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
 
 int tc_conv_backward(Model* m, int B, cudaStream_t s) {
   int r = CFFM_OK;
-  CFFM_DISPATCH_ACT(m->cfg.activation, r = conv_backward_act<ACT>(m, B, s));
+  const bool split = reinterpret_cast<TCState*>(m->tcs)->split;
+  CFFM_DISPATCH_PHI(m->cfg.activation, r = split ? conv_backward_act<ACT, true>(m, B, s) : conv_backward_act<ACT, false>(m, B, s));
   return r;
 }
 
 // debug access for the parity tests: X_{l+1} = phi(Y_l) converted to fp32 [B,Ho,Ho,P]
-__global__ void k_unpad_bf16(const bf16* __restrict__ X, int64_t rows, int P, int Pp, float* __restrict__ out) {
+__global__ void k_unpad_bf16(const bf16* __restrict__ X, const bf16* __restrict__ Xlo, int64_t rows, int P, int Pp, float* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * P) return;
   const int64_t r = e / P; const int c = (int)(e - r * P);
-  out[e] = __bfloat162float(X[r * Pp + c]);
+  out[e] = __bfloat162float(X[r * Pp + c]) + (Xlo ? __bfloat162float(Xlo[r * Pp + c]) : 0.f);
 }
 int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   if (!st) return CFFM_ERR_INVALID;
   const bf16* src = grad ? st->dY[l] : st->X[l + 1];
+  const bf16* src_lo = grad ? st->dYlo[l] : st->Xlo[l + 1];
   if (!src) return CFFM_ERR_INVALID;
-  k_unpad_bf16<<<ceil_div(rows * m->P, 256), 256>>>(src, rows, m->P, st->Pp, dev_out);
+  k_unpad_bf16<<<ceil_div(rows * m->P, 256), 256>>>(src, src_lo, rows, m->P, st->Pp, dev_out);
   return cudaDeviceSynchronize() == cudaSuccess ? CFFM_OK : CFFM_ERR_CUDA;
 }
 

@@ -324,12 +324,12 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
     { CFFM_PROF(m, "sumpool0", s);
     k_sumpool0<<<ceil_div(B, 8), 256, 8 * 2 * F * sizeof(float), s>>>(m->outer_rows, B, F, K, m->t1, m->t1_dim); }
     m->launches++;
-    if (m->cfg.precision == CFFM_PREC_BF16) {
+    if (tc_path(m)) {
       int r = tc_conv_forward(m, B, s);
       if (r != CFFM_OK) return r;
     }
     int off = K;
-    for (int l = 0; l < (m->cfg.precision == CFFM_PREC_BF16 ? 0 : m->n_live); ++l) {
+    for (int l = 0; l < (tc_path(m) ? 0 : m->n_live); ++l) {
       const int Hin = K >> l, Ho = Hin >> 1;
       const std::string tag_f = "conv_fwd_l" + std::to_string(l), tag_s = "sumpool_l" + std::to_string(l + 1);
       if (l == 0) {

@@ -136,7 +136,8 @@ int tc_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K, cu
     g_tc_err = "cuTensorMapEncodeTiled failed";
     return CFFM_ERR_CUDA;
   }
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once();
   if (!attr_done) {
     if (cudaFuncSetAttribute(k_tc<PlainGemm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<PlainGemm>()) != cudaSuccess) {
       g_tc_err = "cudaFuncSetAttribute(smem) failed"; return CFFM_ERR_CUDA;
@@ -167,7 +168,8 @@ int tc_gemm_bf16_tn(const void* A, const void* B, float* C, int M, int N, int R,
     g_tc_err = "cuTensorMapEncodeTiled failed";
     return CFFM_ERR_CUDA;
   }
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;
+  bool& attr_done = attr_once();
   if (!attr_done) {
     if (cudaFuncSetAttribute(k_tc<PlainGemmTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<PlainGemmTN>()) != cudaSuccess) {
       g_tc_err = "cudaFuncSetAttribute(smem) failed"; return CFFM_ERR_CUDA;

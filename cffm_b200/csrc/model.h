@@ -142,6 +142,9 @@ struct Model {
   int64_t ds_N = 0;
 };
 
+// the conv stack runs on the tcgen05 tensor cores (bf16 operands, or split bf16 = hi + lo for fp32-class accuracy)
+inline bool tc_path(const Model* m) { return m->cfg.precision != CFFM_PREC_FP32; }
+
 // ---- implemented across the .cu files ----
 int model_build_layout(Model* m);
 int model_alloc(Model* m);

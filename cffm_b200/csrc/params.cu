@@ -60,8 +60,8 @@ int model_build_layout(Model* m) {
     m->conv_depth = d; m->n_live = d - 1;
     for (int l = 0; l < d; ++l) m->t1_dim += m->Ko >> l;
   }
-  if (c.precision != CFFM_PREC_FP32 && c.precision != CFFM_PREC_BF16) { m->err = "unknown precision"; return CFFM_ERR_INVALID; }
-  if (c.precision == CFFM_PREC_BF16) { int r = tc_supported(m); if (r != CFFM_OK) return r; }
+  if (c.precision != CFFM_PREC_FP32 && c.precision != CFFM_PREC_BF16 && c.precision != CFFM_PREC_BF16X3) { m->err = "unknown precision"; return CFFM_ERR_INVALID; }
+  if (c.precision != CFFM_PREC_FP32) { int r = tc_supported(m); if (r != CFFM_OK) return r; }
   DenseLayout& L = m->lay;
   L = DenseLayout();
   for (int i = 0; i < kMaxConv; ++i) L.conv_w[i] = L.conv_b[i] = -1;
@@ -258,7 +258,7 @@ int model_alloc(Model* m) {
   TRY(dmalloc(m, &m->ids_buf, B * F)); TRY(dmalloc(m, &m->labels_buf, B));
   if (m->cfg.outer_conv) {
     TRY(dmalloc(m, &m->outer_rows, B * F * m->Ko));
-    if (m->cfg.precision == CFFM_PREC_BF16) {
+    if (tc_path(m)) {
       TRY(tc_alloc(m, false));
     } else {
       for (int l = 0; l < m->n_live; ++l) {

@@ -106,6 +106,64 @@ class Engine:
         for k, v in weights.items():
             self.set_param(k, v, accum)
 
+    def opt_slots(self):
+        """Optimizer slots this handle keeps per variable: 1 (Adagrad accumulator / momentum / Adam m) and,
+        for Adam, 2 (v).  Plain gradient descent has none."""
+        opt = int(self.cfg.optimizer)
+        return {OPTIMIZERS["GradientDescentOptimizer"]: 0, OPTIMIZERS["AdamOptimizer"]: 2}.get(opt, 1)
+
+    def get_slot(self, name, slot):
+        """slot 1: ``<name>``, slot 2: ``<name>:2`` of cffm_get_accum (same shape as the variable)."""
+        shape, numel, _ = self._info(name)
+        a = np.empty(numel, dtype=np.float32)
+        key = name if slot == 1 else "%s:%d" % (name, slot)
+        self._check(self.lib.cffm_get_accum(self.h, key.encode(), _ptr(a), numel), "cffm_get_accum")
+        return a.reshape(shape)
+
+    def set_slot(self, name, slot, value):
+        shape, numel, _ = self._info(name)
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float32).reshape(-1))
+        if a.size != numel:
+            raise CffmError("size mismatch for %s: %d vs %d" % (name, a.size, numel))
+        key = name if slot == 1 else "%s:%d" % (name, slot)
+        self._check(self.lib.cffm_set_accum(self.h, key.encode(), _ptr(a), numel), "cffm_set_accum")
+
+    def get_opt_step(self):
+        v = C.c_int64()
+        self._check(self.lib.cffm_get_opt_step(self.h, C.byref(v)), "cffm_get_opt_step")
+        return int(v.value)
+
+    def set_opt_step(self, step):
+        self._check(self.lib.cffm_set_opt_step(self.h, int(step)), "cffm_set_opt_step")
+
+    def state_dict(self):
+        """Everything a resumed run needs: variables (``w:<name>``), optimizer slots (``a:<name>``,
+        ``a2:<name>`` = Adam v) and the optimizer step counter (``opt_step``).  The reference's
+        ``tf.train.Saver`` (CFFM.py:159, :226-228) stores all global variables, i.e. the same set."""
+        out = OrderedDict()
+        for k in self.param_infos():
+            out["w:" + k] = self.get_param(k)
+        for slot in range(1, self.opt_slots() + 1):
+            for k in self.param_infos():
+                out[("a:" if slot == 1 else "a2:") + k] = self.get_slot(k, slot)
+        out["opt_step"] = np.int64(self.get_opt_step())
+        return out
+
+    def load_state_dict(self, state):
+        for k in state:
+            if k == "opt_step":
+                self.set_opt_step(int(state[k]))
+                continue
+            kind, name = k.split(":", 1)
+            if kind == "w":
+                self.set_param(name, state[k])
+            elif kind in ("a", "a2"):
+                slot = 1 if kind == "a" else 2
+                if slot <= self.opt_slots():
+                    self.set_slot(name, slot, state[k])
+            else:
+                raise CffmError("unknown checkpoint entry %r" % (k,))
+
     def init_params(self, seed):
         self._check(self.lib.cffm_init_params(self.h, int(seed)), "cffm_init_params")
 
@@ -201,6 +259,10 @@ class Engine:
             tag, n, ms = line.split()
             out[tag] = (int(n), float(ms))
         return out
+
+    def uses_graph(self):
+        """Whether training steps currently replay from a CUDA graph (CFFM_GRAPH=0 or a failed capture turn it off)."""
+        return bool(self.lib.cffm_uses_graph(self.h))
 
     def launch_count(self):
         return int(self.lib.cffm_launch_count(self.h))

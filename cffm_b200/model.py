@@ -94,15 +94,12 @@ class CFFM:
 
     # ------------------------------------------------------------------ checkpoint (SURVEY next-3)
     def save_state(self, path):
-        w = self.engine.get_weights()
-        a = self.engine.get_weights(accum=True)
-        np.savez(path, **{"w:" + k: v for k, v in w.items()}, **{"a:" + k: v for k, v in a.items()})
+        """Variables, every optimizer slot (Adam: m and v) and the optimizer step counter."""
+        np.savez(path, **self.engine.state_dict())
 
     def load_state(self, path):
         z = np.load(path)
-        for k in z.files:
-            kind, name = k.split(":", 1)
-            self.engine.set_param(name, z[k], accum=(kind == "a"))
+        self.engine.load_state_dict({k: z[k] for k in z.files})
 
     # ------------------------------------------------------------------ training loop
     def train(self, data):
@@ -211,16 +208,21 @@ class CFFM:
         bs = int(self.eval_batch or self.batch_size)
         if isinstance(X, np.ndarray) and X.shape[1] == self.num_field:
             return self.engine.evaluate(X, Y, bs)
-        # ragged rows: the reference stops at the first length change inside a block
-        preds, idx = [], 0
+        # Ragged rows: the reference's block stops at the first length change while the next block still starts at
+        # (k+1)*bs, so rows are skipped and its metric call then fails on the length mismatch (CFFM.py:597-612).
+        # Scored here: exactly the rows the blocks covered, each paired with its own label; the clip bounds come
+        # from the full label vector as in the reference (:609-611).
+        preds, rows, idx = [], [], 0
         blk = self.get_ordered_block_from_data(data, bs, idx)
         while len(blk['X']) > 0:
             preds.append(self.engine.forward(blk['X']))
+            rows.append(np.arange(idx * bs, idx * bs + len(blk['X'])))
             idx += 1
             blk = self.get_ordered_block_from_data(data, bs, idx)
         y_pred = np.concatenate(preds).astype(np.float64)
-        y_true = np.asarray(Y, dtype=np.float64)[: len(y_pred)]
-        pb = np.minimum(np.maximum(y_pred, y_true.min()), y_true.max())
+        y_all = np.asarray(Y, dtype=np.float64)
+        y_true = y_all[np.concatenate(rows)]
+        pb = np.minimum(np.maximum(y_pred, y_all.min()), y_all.max())
         rmse = math.sqrt(float(np.mean((y_true - pb) ** 2)))
         sst = float(np.sum((y_true - y_true.mean()) ** 2))
         r2 = 1.0 - float(np.sum((y_true - pb) ** 2)) / sst if sst > 0 else 0.0

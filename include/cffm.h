@@ -67,8 +67,11 @@ typedef enum cffm_optimizer {
 /* Arithmetic of the conv contraction. */
 typedef enum cffm_precision {
   CFFM_PREC_FP32 = 0, /* fp32 SIMT contraction (reference arithmetic)                         */
-  CFFM_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM,   */
-                      /* fp32 master weights / optimizer state                                */
+  CFFM_PREC_BF16 = 1, /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM,   */
+                      /* fp32 master weights / optimizer state (logits within 1e-2)           */
+  CFFM_PREC_BF16X3 = 2 /* split bf16 on the same tensor cores: every operand as hi + lo bf16,  */
+                      /* a*b = hi*hi + lo*hi + hi*lo in one fp32 TMEM accumulator: fp32-class  */
+                      /* accuracy (logits within 1e-4 of the fp32 graph) at tensor-core speed  */
 } cffm_precision;
 
 /* Mirrors the constructor arguments of class CFFM (CFFM.py:98-101). */
@@ -115,6 +118,14 @@ int cffm_get_accum(cffm_handle* h, const char* name, float* host_dst, int64_t nu
 int cffm_set_accum(cffm_handle* h, const char* name, const float* host_src, int64_t numel);
 /* re-run the initialisers of CFFM.py:257-284 / :459-467 with a seed */
 int cffm_init_params(cffm_handle* h, uint64_t seed);
+/* Optimizer step counter: the `t` of AdamOptimizer's bias correction (beta1_power / beta2_power
+ * non-slot variables [TF-1.14], CFFM.py:519-520).  The other optimizers have no step-dependent
+ * state: they report 0 and ignore the setter.
+ * A checkpoint has to carry it together with the slots ("<name>" = slot 1, "<name>:2" = Adam v
+ * through cffm_get_accum / cffm_set_accum) for a resumed run to equal an uninterrupted one
+ * (the reference's saver, CFFM.py:159 / :226-228, saves all global variables). */
+int cffm_get_opt_step(cffm_handle* h, int64_t* step);
+int cffm_set_opt_step(cffm_handle* h, int64_t step);
 
 /* ---- sess.run(self.out) (CFFM.py:596): ids int32 [B, num_field] row-major -> out float [B] -- */
 int cffm_forward_dev(cffm_handle* h, const int32_t* ids_dev, int64_t B, float* out_dev, void* stream);
@@ -150,6 +161,8 @@ int cffm_last_loss(cffm_handle* h, float* loss_host);
 int cffm_dataset_evaluate(cffm_handle* h, int64_t batch, double* rmse, double* r2);
 
 int cffm_synchronize(cffm_handle* h);
+/* 1 while training steps replay from a CUDA graph (default), 0 after CFFM_GRAPH=0 or a failed capture */
+int cffm_uses_graph(const cffm_handle* h);
 /* number of kernels launched by the library on this handle since creation */
 int64_t cffm_launch_count(const cffm_handle* h);
 

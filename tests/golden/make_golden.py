@@ -31,6 +31,11 @@ CASES = [
     ("f5k8_gelu_mse", 5, 8, 64, 5, "gelu", "mse", 0, 1, 1),
     ("f4k16_prelu_outer", 4, 16, 40, 6, "prelu", "mae", 1, 0, 1),
     ("f7k8_elu_inner", 7, 8, 90, 10, "elu", "hybrid", 1, 1, 0),
+    # outer_dims 16 and 64 of the scoring sweep (BASELINE.json configs[4]; conv_depth = int(log2 K), CFFM.py:373;
+    # inner flatten generalised from the literal 16*2)
+    ("f6k64_selu", 6, 64, 150, 5, "selu", "square_loss", 1, 1, 1),
+    ("f10k16_relu", 10, 16, 200, 8, "relu", "square_loss", 1, 1, 1),
+    ("f3k64_gelu_log", 3, 64, 80, 6, "gelu", "log_loss", 1, 1, 1),
 ]
 
 

@@ -45,7 +45,28 @@ def test_executed_flops_of_the_factorised_layer0_kernels():
     # direct form: other layers, fp32 mode, more than 40 fields
     assert bench.executed_flops(spec, "conv_fwd_l1", 8192, "bf16") is None
     assert bench.executed_flops(spec, "conv_fwd_l0", 8192, "fp32") is None
+    # split bf16: three MMAs per product, direct form on every layer
+    assert bench.executed_flops(spec, "conv_fwd_l0", 8192, "bf16x3") == 3 * algo
+    assert bench.executed_flops(spec, "conv_dgrad_l2", 8192, "bf16x3") == 3 * bench.algorithmic_work(spec, "conv_dgrad_l2", 8192, 1)[1]
+    assert bench.executed_flops(spec, "gather_outer", 8192, "bf16x3") is None
     assert bench.executed_flops(dict(spec, F=44), "conv_fwd_l0", 8192, "bf16") is None
+
+
+def test_both_arms_print_the_same_config():
+    spec = _criteo()
+    a = bench.shared_config(spec, 1)
+    assert a["batch_per_gpu"] == 8192 and a["global_batch"] == 8192 and "l2" in a and a["parallelism"] == "dp1"
+    assert a == bench.shared_config(bench.workload_spec("criteo", 0), 1)
+    assert bench.shared_config(spec, 8)["global_batch"] == 65536
+    flush, text = bench.l2_policy(bench.workload_spec("frappe", 0), 256)
+    assert flush and "flushed" in text
+    assert not bench.l2_policy(spec, 8192)[0]
+
+
+def test_cpu_micro_batch_is_bounded():
+    b = bench.cpu_batch_for(_criteo())
+    assert 8 <= b <= 128 and b & (b - 1) == 0
+    assert bench.cpu_batch_for(bench.workload_spec("frappe", 0)) <= 256
 
 
 def test_ncu_traffic_table_matches_the_bench_workload():

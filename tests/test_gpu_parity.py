@@ -24,6 +24,9 @@ CASES = {
     "f5k8_gelu_mse": (5, 8, 64, 5, "gelu", "mse", 0, 1, 1),
     "f4k16_prelu_outer": (4, 16, 40, 6, "prelu", "mae", 1, 0, 1),
     "f7k8_elu_inner": (7, 8, 90, 10, "elu", "hybrid", 1, 1, 0),
+    "f6k64_selu": (6, 64, 150, 5, "selu", "square_loss", 1, 1, 1),
+    "f10k16_relu": (10, 16, 200, 8, "relu", "square_loss", 1, 1, 1),
+    "f3k64_gelu_log": (3, 64, 80, 6, "gelu", "log_loss", 1, 1, 1),
 }
 
 
@@ -363,3 +366,29 @@ def test_cli_train_loop_runs_on_the_fixture(tmp_path, monkeypatch):
     assert len(model.valid_rmse) >= 6 and min(model.valid_rmse) < model.valid_rmse[0]
     assert min(model.valid_rmse) < 1.0
     assert len(model.train_rmse) == len(model.valid_rmse) == len(model.test_rmse) == len(model.valid_r2)
+
+
+@pytest.mark.parametrize("F,K,N,act", [(3, 64, 70000, "elu"), (10, 16, 66000, "selu")])
+def test_evaluate_at_65536_blocks_k16_k64(F, K, N, act):
+    """Scoring sweep of BASELINE.json configs[4] (B up to 65 536, K = 16 / 64): evaluate() in blocks of 65 536
+    (one full block + a partial one) against the oracle scoring the same rows in blocks of 4 096 -- the metric does
+    not depend on the block size (CFFM.py:583-615)."""
+    from cffm_b200 import Engine
+    from oracle.cffm_ref import evaluate
+    rng = np.random.default_rng(7)
+    M = 5000
+    ids = rng.integers(0, M, (N, F)).astype(np.int32)
+    y = rng.choice([-1.0, 1.0], N).astype(np.float32)
+    eng = Engine(M, F, K, K, activation=act, max_batch=65536, seed=9)
+    eng.set_param("feature_bias", rng.normal(0, 0.3, (M, 1)).astype(np.float32))
+    eng.set_param("outer_embeddings", rng.normal(0, 0.2, (M, K)).astype(np.float32))
+    ref = _oracle_like(eng, M, F, K, act, dtype=torch.float32)
+    rmse, r2 = eng.evaluate(ids, y, 65536)
+    small = eng.evaluate(ids, y, 4096)
+    assert abs(rmse - small[0]) < 1e-5 and abs(r2 - small[1]) < 1e-4          # block-size independence on the device
+    want = evaluate(ref, {"X": ids, "Y": list(y)}, 4096)
+    assert abs(rmse - want[0]) < 1e-4 * max(1.0, want[0]) and abs(r2 - want[1]) < 1e-3 * max(1.0, abs(want[1])), (rmse, r2, want)
+    out = eng.forward(ids[:65536])
+    ref_out = ref.predict(ids[:2048]).reshape(-1).numpy()
+    assert _relerr(out[:2048], ref_out) < 1e-4
+    eng.close()
