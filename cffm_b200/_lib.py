@@ -17,11 +17,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcffm_b200.so")
 BUILD_DIR = os.path.join(ROOT, "build")
 
-CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu", "gemm_tc.cu", "conv_tc.cu"]
+CU_SOURCES = ["params.cu", "forward.cu", "backward.cu", "update.cu", "api.cu", "comm.cu", "shard.cu", "gemm_tc.cu", "conv_tc.cu"]
 CPP_SOURCES = ["libfm.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ACTIVATIONS = {"relu": 0, "elu": 1, "selu": 2, "prelu": 3, "gelu": 4}
 LOSSES = {"square_loss": 0, "log_loss": 1, "mse": 2, "mae": 3, "hybrid": 4}
 OPTIMIZERS = {"AdagradOptimizer": 0, "GradientDescentOptimizer": 1, "MomentumOptimizer": 2, "AdamOptimizer": 3}
@@ -40,6 +40,7 @@ class Config(C.Structure):
         ("loss_type", C.c_int32), ("optimizer", C.c_int32), ("precision", C.c_int32),
         ("lr", C.c_float), ("lamda", C.c_float), ("lamda_att", C.c_float), ("beta_outer", C.c_float),
         ("max_batch", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+        ("shard_world", C.c_int32), ("shard_rank", C.c_int32),
     ]
 
 

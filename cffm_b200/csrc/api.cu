@@ -59,6 +59,7 @@ extern "C" int cffm_create(const cffm_config* cfg, cffm_handle** out) {
   if (r != CFFM_OK) { g_err = m->err; model_free(m); delete h; return r; }
   const char* eg = getenv("CFFM_GRAPH");
   m->use_graph = !(eg && eg[0] == '0');
+  if (sharded(m)) m->use_graph = false;   // the row exchange reads its counts on the host: the step is not one graph
   *out = h;
   return CFFM_OK;
   API_END((cffm_handle*)nullptr)

@@ -127,7 +127,8 @@ struct Dgrad0Args {
   float* g_rows;
   int F, P, K, lgHo;
 };
-__global__ void k_dgrad0(const Dgrad0Args a) {
+// (K = 64: one thread per output position is 1024 threads, so the kernel has to fit 64 registers)
+__global__ void __launch_bounds__(1024, 1) k_dgrad0(const Dgrad0Args a) {
   extern __shared__ __align__(16) float sm[];
   const int T = blockDim.x, t = threadIdx.x, K = a.K, F = a.F, P = a.P;
   const int Ho = 1 << a.lgHo;
@@ -514,7 +515,7 @@ int model_alloc_train(Model* m) {
   // sparse update scratch; under data parallelism the global batch is updated on every rank
   m->upd_cap = (int64_t)m->world * B * F;
   if (sparse_work_alloc(&m->sw, m->upd_cap, &m->err) != CFFM_OK) return CFFM_ERR_NOMEM;
-  if (m->world > 1) {
+  if (m->world > 1 && !sharded(m)) {
     TRY(dmalloc(m, &m->all_ids, m->upd_cap));
     if (m->cfg.inner_conv) TRY(dmalloc(m, &m->all_g_inner, m->upd_cap * m->Ki));
     if (m->cfg.outer_conv) TRY(dmalloc(m, &m->all_g_outer, m->upd_cap * m->Ko));
@@ -549,8 +550,11 @@ static void launch_colsum(Model* m, const float* X, int64_t rows, int ld, int n,
 }
 
 // Everything after the forward pass of a training step.  The loss sum is already in scalars[0].
-int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64_t B64, cudaStream_t s) {
+int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, int64_t B64, cudaStream_t s) {
   (void)labels;
+  // the rows the forward pass computed on (row-sharded tables: the received list and the renumbered ids)
+  const TableView tv = m->view;
+  const int32_t* ids = sharded(m) ? tv.ids : ids_in;
   const int B = (int)B64, F = m->F, P = m->P;
   const DenseLayout& L = m->lay;
   const float* w = m->dense_w;
@@ -562,9 +566,10 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   // ---- loss: (global) sum -> loss value, scale of dLoss/dout ----
   if (m->cfg.lamda > 0.f && m->cfg.loss_type == CFFM_LOSS_SQUARE) {  // regulariser terms of CFFM.py:489-491
     CFFM_PROF(m, "l2_reg_sums", s);
-    if (m->cfg.inner_conv) launch_sumsq(m->inner_tab, (int64_t)m->M * m->Ki, m->sumsq_partial, m->scalars + 6, s);
-    if (m->cfg.outer_conv) launch_sumsq(m->outer_tab, (int64_t)m->M * m->Ko, m->sumsq_partial, m->scalars + 7, s);
+    if (m->cfg.inner_conv) launch_sumsq(m->inner_tab, m->Mloc * m->Ki, m->sumsq_partial, m->scalars + 6, s);
+    if (m->cfg.outer_conv) launch_sumsq(m->outer_tab, m->Mloc * m->Ko, m->sumsq_partial, m->scalars + 7, s);
     m->launches += 4;
+    if (sharded(m)) { int r = comm_allreduce_f32(m, m->scalars + 6, 2, s); if (r != CFFM_OK) return r; }   // shards -> whole tables
   }
   launch_loss_sum(m, B, s);
   if (m->world > 1) { int r = comm_allreduce_f32(m, m->scalars, 1, s); if (r != CFFM_OK) return r; }
@@ -636,7 +641,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     InnerLinBwdArgs a;
     a.ids = ids; a.B = B; a.F = F; a.P = P; a.K = m->cfg.inner_conv ? m->Ki : 4; a.lgK = ilog2(a.K);
     a.n_small = m->n_small; a.inner_conv = m->cfg.inner_conv; a.linear_att = m->cfg.linear_att;
-    a.tab = m->inner_tab; a.fbias = m->fbias_tab; a.cw = w + L.iconv_w; a.cb = w + L.iconv_b; a.Wd = w + L.din_k;
+    a.tab = tv.inner; a.fbias = tv.fbias; a.cw = w + L.iconv_w; a.cb = w + L.iconv_b; a.Wd = w + L.din_k;
     a.attW = w + L.att_W; a.attb = w + L.att_b; a.w3 = w + L.d3_k;
     a.pair_i = m->pair_i; a.pair_j = m->pair_j; a.tau = m->cfg.lamda_att; a.gout = m->gout;
     a.g_inner_rows = m->g_inner_rows; a.g_bias_rows = m->g_bias_rows; a.rowbuf = m->rowbuf;
@@ -649,7 +654,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     if (m->cfg.inner_conv) {
       InnerDenseGradArgs d;
       d.ids = ids; d.B = B; d.F = F; d.P = P; d.K = m->Ki; d.lgK = ilog2(m->Ki);
-      d.tab = m->inner_tab; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
+      d.tab = tv.inner; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
       d.pair_i = m->pair_i; d.pair_j = m->pair_j; d.partial = part + pl.off_Wd; d.C = pl.Cb;
       dim3 grid(ceil_div((int64_t)P * m->Ki, 256), pl.Cb);
       CFFM_PROF(m, "inner_dense_grad", s);
@@ -683,6 +688,19 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
   const int32_t* upd_ids = ids;
   const float *gi = m->g_inner_rows, *go = m->g_outer_rows, *gbr = m->g_bias_rows;
   int64_t n_upd = (int64_t)B * F;
+  if (sharded(m)) {
+    // row-sharded tables: dense gradients are summed over the ranks; gradient rows go to the owners of the rows
+    { CFFM_PROF(m, "dp_allreduce", s);
+      int r = comm_allreduce_f32(m, g, L.total, s); if (r != CFFM_OK) return r; }
+    int r = shard_backward_update(m, B64, s); if (r != CFFM_OK) return r;
+    const int opt = m->cfg.optimizer;
+    const float* lr_dev = opt == CFFM_OPT_ADAM ? m->scalars + 4 : nullptr;
+    CFFM_PROF(m, "dense_adagrad", s);
+    launch_dense_update(m->dense_w, opt == CFFM_OPT_SGD ? nullptr : m->dense_acc, m->dense_acc2, g, L.total, opt, m->cfg.lr, lr_dev, s);
+    m->launches++;
+    CFFM_CUDA_OK(m, cudaGetLastError());
+    return CFFM_OK;
+  }
   if (m->world > 1) {
     CFFM_PROF(m, "dp_allreduce_allgather", s);
     // the group is closed on every exit path (an open NCCL group inside a stream capture poisons the communicator)
@@ -713,7 +731,7 @@ int run_backward_update(Model* m, const int32_t* ids, const float* labels, int64
     if (adam) { launch_adam_tick(m->scalars, m->cfg.lr, s); m->launches++; }
     const float* lr_dev = adam ? m->scalars + 4 : nullptr;
     SparseTables t;
-    t.rowmap = m->rowmap; t.M = m->M;
+    t.rowmap = m->rowmap; t.M = m->Mloc;
     int j = 0;
     // Adam's sparse apply moves every row; the l2 regulariser makes the two embedding gradients dense (Q9:
     // the outer table is regularised by lamda_att)

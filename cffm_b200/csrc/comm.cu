@@ -19,6 +19,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
@@ -41,6 +43,8 @@ static bool nccl_load() {
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
   SYM(AllGather, "ncclAllGather");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
   SYM(GetErrorString, "ncclGetErrorString");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
@@ -67,6 +71,20 @@ int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_ran
   return CFFM_OK;
 }
 
+// Point-to-point halves of the all-to-alls of the row-sharded tables (shard.cu); always issued inside a group.
+int comm_send(Model* m, const void* buf, int64_t bytes, int peer, cudaStream_t s) {
+  if (!m->comm) { m->err = "communicator not initialised"; return CFFM_ERR_COMM; }
+  ncclResult_t r = g_nccl.Send(buf, (size_t)bytes, ncclInt8, peer, m->comm->comm, s);
+  if (r != ncclSuccess) { m->err = std::string("ncclSend: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
+  return CFFM_OK;
+}
+int comm_recv(Model* m, void* buf, int64_t bytes, int peer, cudaStream_t s) {
+  if (!m->comm) { m->err = "communicator not initialised"; return CFFM_ERR_COMM; }
+  ncclResult_t r = g_nccl.Recv(buf, (size_t)bytes, ncclInt8, peer, m->comm->comm, s);
+  if (r != ncclSuccess) { m->err = std::string("ncclRecv: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
+  return CFFM_OK;
+}
+
 // The collectives of one step (dense all-reduce + the row all-gathers) go out as ONE NCCL group: one fused launch
 // instead of five back-to-back kernels.
 int comm_group_begin(Model* m) {
@@ -78,6 +96,7 @@ int comm_group_begin(Model* m) {
 int comm_group_end(Model* m) {
   ncclResult_t r = g_nccl.GroupEnd();
   if (r != ncclSuccess) { m->err = std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(r); return CFFM_ERR_COMM; }
+  m->launches++;   // a group goes out as one fused kernel
   return CFFM_OK;
 }
 
@@ -121,5 +140,9 @@ extern "C" int cffm_comm_init(cffm_handle* h, const char id[128], int32_t rank, 
     return CFFM_ERR_COMM;
   }
   m->world = world; m->rank = rank;
+  if (sharded(m) && (world != m->shard_world || rank != m->shard_rank)) {
+    m->err = "cffm_comm_init: rank / world differ from cfg.shard_rank / cfg.shard_world";
+    return CFFM_ERR_INVALID;
+  }
   return CFFM_OK;
 }

@@ -293,17 +293,22 @@ static void launch_gemm(Model* m, const Prob& prob, int nsplit, cudaStream_t s) 
 
 static int ilog2(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
 
-int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, cudaStream_t s) {
+int run_forward(Model* m, const int32_t* ids_in, const float* labels, int64_t B64, cudaStream_t s) {
   const bool for_train = labels != nullptr;
   const int B = (int)B64, F = m->F, P = m->P;
   const DenseLayout& L = m->lay;
   const float* w = m->dense_w;
+  // row-sharded tables: fetch the rows of this batch from their owners; the step then runs on that list
+  TableView tv; tv.inner = m->inner_tab; tv.outer = m->outer_tab; tv.fbias = m->fbias_tab; tv.ids = ids_in;
+  if (sharded(m)) { int r = shard_forward_exchange(m, ids_in, B64, s, &tv); if (r != CFFM_OK) return r; }
+  m->view = tv;
+  const int32_t* ids = tv.ids;
   // ---- inner path + linear term ----
   {
     InnerLinArgs a;
     a.ids = ids; a.B = B; a.F = F; a.P = P; a.K = m->cfg.inner_conv ? m->Ki : 4; a.lgK = ilog2(a.K);
     a.inner_conv = m->cfg.inner_conv; a.linear_att = m->cfg.linear_att;
-    a.tab = m->inner_tab; a.fbias = m->fbias_tab;
+    a.tab = tv.inner; a.fbias = tv.fbias;
     a.cw = w + L.iconv_w; a.cb = w + L.iconv_b; a.Wd = w + L.din_k; a.bd = w + L.din_b;
     a.attW = w + L.att_W; a.attb = w + L.att_b; a.w3 = w + L.d3_k; a.b3 = w + L.d3_b;
     a.pair_i = m->pair_i; a.pair_j = m->pair_j; a.tau = m->cfg.lamda_att;
@@ -319,7 +324,7 @@ int run_forward(Model* m, const int32_t* ids, const float* labels, int64_t B64, 
   // ---- outer path ----
   if (m->cfg.outer_conv) {
     const int K = m->Ko;
-    { CFFM_PROF(m, "gather_outer", s); launch_gather_rows(m->outer_tab, ids, (int64_t)B * F, K, m->outer_rows, s); }
+    { CFFM_PROF(m, "gather_outer", s); launch_gather_rows(tv.outer, ids, (int64_t)B * F, K, m->outer_rows, s); }
     m->launches++;
     { CFFM_PROF(m, "sumpool0", s);
     k_sumpool0<<<ceil_div(B, 8), 256, 8 * 2 * F * sizeof(float), s>>>(m->outer_rows, B, F, K, m->t1, m->t1_dim); }

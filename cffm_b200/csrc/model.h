@@ -38,11 +38,22 @@ struct DenseLayout {
   int64_t total = 0;
 };
 
-struct Comm;  // NCCL state (comm.cu)
+// tables and ids a step computes on: the handle's own tables, or (row-sharded tables) the rows received from their
+// owners with the ids renumbered to positions in that list
+struct TableView { const float *inner = nullptr, *outer = nullptr, *fbias = nullptr; const int32_t* ids = nullptr; };
+
+struct Comm;        // NCCL state (comm.cu)
+struct ShardState;  // row-sharded tables: exchange buffers and per-step counts (shard.cu)
 
 struct Model {
   cffm_config cfg;
   int F, P, Ki, Ko, M;
+  // row-sharded tables (cfg.shard_world > 1): this handle stores rows r with r % shard_world == shard_rank as local
+  // row r / shard_world; Mloc rows here, at most Mloc_max on any rank.  Replicated: Mloc == Mloc_max == M.
+  int shard_world = 1, shard_rank = 0;
+  int64_t Mloc = 0, Mloc_max = 0;
+  ShardState* shard = nullptr;
+  TableView view;        // of the last forward pass (the backward pass reads the same rows)
   int conv_depth;  // int(log2 Ko), CFFM.py:373
   int n_live;      // conv layers that reach the output = conv_depth - 1
   int t1_dim;      // sum_{l<conv_depth} Ko >> l   (= 2K-2)
@@ -165,7 +176,14 @@ int tc_conv_forward(Model* m, int B, cudaStream_t s);
 int tc_conv_backward(Model* m, int B, cudaStream_t s);
 int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows);
 
+inline bool sharded(const Model* m) { return m->shard_world > 1; }
+int shard_forward_exchange(Model* m, const int32_t* ids_dev, int64_t B, cudaStream_t s, TableView* view);
+int shard_backward_update(Model* m, int64_t B, cudaStream_t s);
+void shard_free(Model* m);
+
 int comm_allreduce_f32(Model* m, float* buf, int64_t n, cudaStream_t s);
+int comm_send(Model* m, const void* buf, int64_t bytes, int peer, cudaStream_t s);
+int comm_recv(Model* m, void* buf, int64_t bytes, int peer, cudaStream_t s);
 int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_rank, cudaStream_t s);
 int comm_group_begin(Model* m);
 int comm_group_end(Model* m);

@@ -44,6 +44,13 @@ int model_build_layout(Model* m) {
   if (c.inner_conv && !pow2(m->Ki)) { m->err = "inner_dims must be a power of two in [4,64]"; return CFFM_ERR_INVALID; }
   if (c.outer_conv && !pow2(m->Ko)) { m->err = "outer_dims must be a power of two in [4,64]"; return CFFM_ERR_INVALID; }
   if (c.max_batch < 1) { m->err = "max_batch must be positive"; return CFFM_ERR_INVALID; }
+  m->shard_world = c.shard_world > 1 ? c.shard_world : 1;
+  m->shard_rank = c.shard_world > 1 ? c.shard_rank : 0;
+  if (m->shard_rank < 0 || m->shard_rank >= m->shard_world) { m->err = "shard_rank outside [0, shard_world)"; return CFFM_ERR_INVALID; }
+  m->Mloc_max = ((int64_t)m->M + m->shard_world - 1) / m->shard_world;
+  m->Mloc = ((int64_t)m->M - m->shard_rank + m->shard_world - 1) / m->shard_world;   // rows r < M with r % world == rank
+  if (m->Mloc < 1) { m->err = "features_M is smaller than shard_world"; return CFFM_ERR_INVALID; }
+  if (m->Mloc_max * m->shard_world >= (1ll << 31)) { m->err = "features_M too large for 32-bit row keys"; return CFFM_ERR_INVALID; }
   if (c.activation < 0 || c.activation > CFFM_ACT_GELU) { m->err = "unknown activation"; return CFFM_ERR_INVALID; }
   if (c.loss_type < 0 || c.loss_type > CFFM_LOSS_HYBRID) { m->err = "unknown loss_type"; return CFFM_ERR_INVALID; }
   if (c.optimizer < 0 || c.optimizer > CFFM_OPT_ADAM) { m->err = "unknown optimizer"; return CFFM_ERR_INVALID; }
@@ -65,7 +72,7 @@ int model_build_layout(Model* m) {
   DenseLayout& L = m->lay;
   L = DenseLayout();
   for (int i = 0; i < kMaxConv; ++i) L.conv_w[i] = L.conv_b[i] = -1;
-  const int64_t F = m->F, P = m->P, M = m->M;
+  const int64_t F = m->F, P = m->P, M = m->Mloc;   // table shapes are those of the local shard
   int dense_idx = 0;
   auto dense_name = [&]() { std::string n = dense_idx == 0 ? "dense" : "dense_" + std::to_string(dense_idx); ++dense_idx; return n; };
   if (c.inner_conv) add_param(m, "inner_embeddings", {M, m->Ki}, PK_TABLE_INNER, nullptr, true);
@@ -134,10 +141,14 @@ __device__ __forceinline__ float normal_at(uint64_t key, uint64_t idx, uint32_t 
 
 enum InitKind { INIT_CONST = 0, INIT_NORMAL = 1, INIT_TRUNC_NORMAL = 2, INIT_UNIFORM = 3 };
 
-__global__ void k_init(float* __restrict__ dst, int64_t n, int kind, float a, uint64_t key) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Tables of a sharded handle (world > 1): local element (lr, c) of a [Mloc, K] shard is element
+// ((lr * world + rank) * K + c) of the full table, so every rank draws exactly the values the replicated layout has.
+__global__ void k_init(float* __restrict__ dst, int64_t n, int kind, float a, uint64_t key, int K, int world, int rank) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
+  for (; e < n; e += stride) {
+    int64_t i = e;
+    if (world > 1) { const int64_t lr = e / K; i = (lr * world + rank) * K + (e - lr * K); }
     float v;
     if (kind == INIT_CONST) v = a;
     else if (kind == INIT_NORMAL) v = a * normal_at(key, (uint64_t)i, 0);
@@ -148,27 +159,27 @@ __global__ void k_init(float* __restrict__ dst, int64_t n, int kind, float a, ui
     } else {  // uniform(-a, a): glorot_uniform of tf.layers.dense [TF-1.14]
       v = a * (2.f * u01(splitmix64(key ^ splitmix64((uint64_t)i))) - 1.f);
     }
-    dst[i] = v;
+    dst[e] = v;
   }
 }
 
-static void launch_init(Model* m, float* dst, int64_t n, int kind, float a, uint64_t key) {
+static void launch_init(Model* m, float* dst, int64_t n, int kind, float a, uint64_t key, int table_K = 0) {
   if (n <= 0) return;
   int blocks = (int)((n + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  k_init<<<blocks, 256, 0, m->stream>>>(dst, n, kind, a, key);
+  k_init<<<blocks, 256, 0, m->stream>>>(dst, n, kind, a, key, table_K > 0 ? table_K : 1, table_K > 0 ? m->shard_world : 1, m->shard_rank);
   m->launches++;
 }
 
 int model_init_params(Model* m, uint64_t seed) {
   const DenseLayout& L = m->lay;
-  const int64_t F = m->F, P = m->P, M = m->M;
+  const int64_t F = m->F, P = m->P, M = m->Mloc;
   uint64_t k = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
   auto key = [&](int i) { return k + 0x632BE59BD9B4E019ull * (uint64_t)(i + 1); };
   float* w = m->dense_w;
   CFFM_CUDA_OK(m, cudaMemsetAsync(m->dense_w, 0, sizeof(float) * m->lay.total, m->stream));
-  if (m->cfg.inner_conv) launch_init(m, m->inner_tab, M * m->Ki, INIT_NORMAL, 0.1f, key(0));     // :257-259
+  if (m->cfg.inner_conv) launch_init(m, m->inner_tab, M * m->Ki, INIT_NORMAL, 0.1f, key(0), m->Ki);     // :257-259
   if (m->cfg.outer_conv) {
-    launch_init(m, m->outer_tab, M * m->Ko, INIT_NORMAL, 0.01f, key(1));                         // :264-266
+    launch_init(m, m->outer_tab, M * m->Ko, INIT_NORMAL, 0.01f, key(1), m->Ko);                         // :264-266
     launch_init(m, w + L.outer_W, P, INIT_TRUNC_NORMAL, 1.f, key(2));                            // :271
     launch_init(m, w + L.outer_b, 1, INIT_TRUNC_NORMAL, 1.f, key(3));                            // :272
   }
@@ -222,7 +233,7 @@ static int dmalloc(Model* m, T** p, int64_t n) {
 #define TRY(x) do { int _r = (x); if (_r != CFFM_OK) return _r; } while (0)
 
 int model_alloc(Model* m) {
-  const int64_t B = m->max_batch, F = m->F, P = m->P, M = m->M;
+  const int64_t B = m->max_batch, F = m->F, P = m->P, M = m->Mloc;
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   CFFM_CUDA_OK(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   if (m->cfg.inner_conv) { TRY(dmalloc(m, &m->inner_tab, M * m->Ki)); TRY(dmalloc(m, &m->inner_acc, M * m->Ki)); }
@@ -295,6 +306,7 @@ void model_free(Model* m) {
                  m->partials, m->fb_buf, m->all_ids, m->all_g_inner, m->all_g_outer, m->all_g_bias, m->reduce_descs,
                  m->eval_acc, m->inner_acc2, m->outer_acc2, m->fbias_acc2, m->dense_acc2, m->rowmap, m->sumsq_partial};
   sparse_work_free(&m->sw);
+  shard_free(m);
   tc_free(m);
   void* ds[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
   for (void* p : ds) if (p) cudaFree(p);

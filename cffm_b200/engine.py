@@ -23,7 +23,9 @@ class Engine:
     def __init__(self, features_M, num_field, inner_dims=32, outer_dims=32, activation="relu",
                  loss_type="square_loss", lamda=0.0, lamda_att=1.0, lr=0.05, linear_att=1, att_dim=0,
                  inner_conv=1, outer_conv=1, beta_outer=1.0, optimizer="AdagradOptimizer", max_batch=1024,
-                 precision="fp32", device=0, seed=2021):
+                 precision="fp32", device=0, seed=2021, shard=None):
+        """``shard=(rank, world)``: row-sharded tables -- this handle owns the rows ``r`` with ``r % world == rank``
+        (local row ``r // world``); ``comm_init(id, rank, world)`` must follow before the first forward."""
         self.lib = _lib.load()
         if att_dim not in (0, num_field) and linear_att:
             # tf.matmul([B,F],[att_dim,att_dim]) only type-checks for att_dim == num_field (SURVEY Q8)
@@ -40,7 +42,10 @@ class Engine:
             outer_conv=int(outer_conv), linear_att=int(linear_att), activation=ACTIVATIONS[activation],
             loss_type=LOSSES[loss_type], optimizer=OPTIMIZERS[optimizer], precision=PRECISIONS[precision],
             lr=float(lr), lamda=float(lamda), lamda_att=float(lamda_att), beta_outer=float(beta_outer),
-            max_batch=int(max_batch), device=int(device), seed=int(seed))
+            max_batch=int(max_batch), device=int(device), seed=int(seed),
+            shard_world=int(shard[1]) if shard else 0, shard_rank=int(shard[0]) if shard else 0)
+        self.shard = (int(shard[0]), int(shard[1])) if shard and int(shard[1]) > 1 else None
+        self.features_M = int(features_M)
         self.cfg = cfg
         self.F = int(num_field)
         self.max_batch = int(max_batch)
@@ -163,6 +168,20 @@ class Engine:
                     self.set_slot(name, slot, state[k])
             else:
                 raise CffmError("unknown checkpoint entry %r" % (k,))
+
+    # ------------------------------------------------------------------ row-sharded tables
+    TABLES = ("inner_embeddings", "outer_embeddings", "feature_bias")
+
+    def owned_rows(self):
+        """Global row numbers of this handle's table rows, in local order."""
+        if not self.shard:
+            return np.arange(self.features_M)
+        rank, world = self.shard
+        return np.arange(rank, self.features_M, world)
+
+    def set_table_from_global(self, name, full, accum=False):
+        """Load this handle's rows of a full [features_M, K] table (variable or optimizer slot 1)."""
+        self.set_param(name, np.asarray(full)[self.owned_rows()], accum)
 
     def init_params(self, seed):
         self._check(self.lib.cffm_init_params(self.h, int(seed)), "cffm_init_params")

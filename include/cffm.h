@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CFFM_ABI_VERSION 1
+#define CFFM_ABI_VERSION 2
 
 typedef enum cffm_status {
   CFFM_OK = 0,
@@ -95,6 +95,13 @@ typedef struct cffm_config {
   int32_t max_batch;     /* largest B a single launch will see (workspace size) */
   int32_t device;        /* CUDA device ordinal                                */
   uint64_t seed;         /* parameter initialisation seed (reference: unseeded) */
+  /* Row-sharded tables (new; the reference is single-device): with shard_world = G > 1 this handle owns the rows
+   * r of inner_embeddings / outer_embeddings / feature_bias (and of their optimizer slots) with r % G == shard_rank,
+   * stored densely as local row r / G; every gather and every update of a step then goes through an all-to-all
+   * with the owners (cffm_comm_init must be called with the same rank / world before the first forward).
+   * 0 or 1: tables replicated on every rank. */
+  int32_t shard_world;
+  int32_t shard_rank;
 } cffm_config;
 
 typedef struct cffm_handle cffm_handle;
@@ -208,8 +215,14 @@ int cffm_debug_dense_grad(cffm_handle* h, const char* name, float* host_dst, int
  * rank 0 calls cffm_comm_unique_id and ships the 128 bytes to the other ranks (the Python host
  * does that with torch.distributed); every rank then calls cffm_comm_init.  After that
  * cffm_train_step_* treats its batch as one shard of a global batch of world*B samples:
- * dense gradients and the loss sum are all-reduced, touched rows are all-gathered, every rank
- * applies the identical update. */
+ * dense gradients and the loss sum are all-reduced; replicated tables: touched rows are all-gathered and every
+ * rank applies the identical update; row-sharded tables (cfg.shard_world > 1): per step
+ *   forward   unique ids of the local batch, bucketed by owner -> all-to-all -> owners gather their rows ->
+ *             all-to-all back -> the step runs on the received rows
+ *   backward  gradient rows summed per unique id on the requesting rank FIRST -> all-to-all to the owners ->
+ *             owner-side sort + segment sum (ranks in order) + sparse optimizer update of its shard.
+ * With sharded tables cffm_forward_* / cffm_evaluate_* are collective too: every rank must make the same
+ * sequence of calls (batch sizes may differ). */
 int cffm_comm_unique_id(char id_out[128]);
 int cffm_comm_init(cffm_handle* h, const char id[128], int32_t rank, int32_t world);
 

@@ -46,4 +46,5 @@ def test_create_fails_loudly_without_a_device(lib):
 
 
 def test_config_struct_layout():
-    assert C.sizeof(_lib.Config) == 12 * 4 + 4 * 4 + 2 * 4 + 8
+    assert C.sizeof(_lib.Config) == 12 * 4 + 4 * 4 + 2 * 4 + 8 + 2 * 4   # ... + shard_world, shard_rank (ABI version 2)
+    assert _lib.ABI_VERSION == 2

@@ -31,3 +31,27 @@ def test_data_parallel_equals_single_gpu(tmp_path, precision):
     lim = 0.02 if precision == "fp32" else 0.2
     bad = {k: v for k, v in res["frac_over_2e-3"].items() if v > lim}
     assert not bad, bad
+
+
+@pytest.mark.timeout(280)
+@pytest.mark.parametrize("precision,optimizer", [("fp32", "AdagradOptimizer"), ("bf16", "AdagradOptimizer"), ("fp32", "AdamOptimizer")])
+def test_row_sharded_tables_equal_single_gpu(tmp_path, precision, optimizer):
+    """BASELINE.json configs[3] "row-sharded data-parallel": rows move by all-to-all, tables are never replicated."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    out = tmp_path / "shard.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(HERE, "shard_worker.py"), str(out), precision, optimizer]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=260)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["local_rows"] == 351                     # 701 rows over two ranks: 351 + 350
+    assert res["untouched_rows_bit_identical"] and res["init_identical"]
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    for a, b in zip(res["losses"], res["ref_losses"]):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (res["losses"], res["ref_losses"])
+    assert res["pred_max_abs_diff"] <= (2e-2 if precision == "fp32" else 0.2) * max(1.0, res["pred_scale"]), res
+    lim = 0.02 if precision == "fp32" else 0.2
+    bad = {k: v for k, v in res["frac_over_2e-3"].items() if v > lim}
+    assert not bad, bad
