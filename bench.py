@@ -65,6 +65,9 @@ def parse():
                          "the other tensor-core mode; 'none'")
     ap.add_argument("--workloads", default=os.environ.get("CFFM_BENCH_WORKLOADS", "auto"),
                     help="extra workload records: comma list, 'auto' (frappe,ml-tag,book-crossing at N=1 on the criteo run), 'none'")
+    ap.add_argument("--tables", default=os.environ.get("CFFM_BENCH_TABLES", "auto"), choices=["auto", "replicated", "sharded"],
+                    help="N > 1: embedding tables replicated (touched-row all-gather) or row-sharded (all-to-all of rows); "
+                         "auto = sharded for the Criteo shape (BASELINE.json configs[3]), replicated for the small tables")
     ap.add_argument("--l2", default="auto", choices=["auto", "flush", "none"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--cpu-batch", type=int, default=0)
@@ -281,7 +284,15 @@ class Job:
         self.flush_buf.zero_()
 
 
-def measure(job, args, wl_name, precision, steps, warmup, batch=0, profile=True, sample_clocks=False, use_world=True):
+def tables_mode(args, wl_name, world):
+    if world == 1:
+        return "single"
+    if args.tables != "auto":
+        return args.tables
+    return "sharded" if wl_name == "criteo" else "replicated"
+
+
+def measure(job, args, wl_name, precision, steps, warmup, batch=0, profile=True, sample_clocks=False, use_world=True, tables=None):
     """One workload in one arithmetic: device-timed value, end-to-end value, per-kernel table, roofline."""
     torch, dist = job.torch, job.dist
     from cffm_b200 import Engine, comm_unique_id, synth
@@ -292,7 +303,9 @@ def measure(job, args, wl_name, precision, steps, warmup, batch=0, profile=True,
     n_pool = 8
     ids, _ = synth.make_ids(wl_name, n_pool * B, seed=2021 + 17 * rank)
     labels = synth.make_labels(n_pool * B, seed=2021 + 17 * rank)
-    eng = Engine(M, F, K, K, activation=spec["activation"], max_batch=B, precision=precision, device=job.local, seed=2021)
+    tables = tables or tables_mode(args, wl_name, world)
+    eng = Engine(M, F, K, K, activation=spec["activation"], max_batch=B, precision=precision, device=job.local, seed=2021,
+                 shard=(rank, world) if (tables == "sharded" and world > 1) else None)
     if world > 1:
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -383,7 +396,7 @@ def measure(job, args, wl_name, precision, steps, warmup, batch=0, profile=True,
                 "d2h_bytes_per_step": 4, "api": "cffm_train_submit_host (pinned double buffer)"},
         "gpu_launches": int(launches), "roofline": roof, "kernels": kernel_table, "clocks": clocks,
         "wall_s_timed_region": round(t_wall, 4), "final_loss": final_loss, "cuda_graph": uses_graph,
-        "l2": l2_text, "precision": precision,
+        "l2": l2_text, "precision": precision, "tables": tables,
     }
 
 
@@ -421,11 +434,17 @@ def run_ours(args):
         modes[prec] = brief(measure(job, args, args.workload, prec, st, 3, batch=args.batch))
 
     # ---- strong scaling beside the weak one: the global batch of the N=1 run split over the ranks ----
-    strong = None
+    strong, other_tables = None, None
     if world > 1 and B % world == 0 and args.workload == "criteo":
         r = measure(job, args, args.workload, primary, steps, 3, batch=B // world, profile=False)
         strong = {"global_batch": B, "batch_per_gpu": B // world, "value": r["value"], "ms_per_step": r["ms_per_step"],
-                  "e2e": r["e2e"], "note": "fixed global batch (strong scaling); `value` above is weak scaling"}
+                  "e2e": r["e2e"], "tables": r["tables"], "note": "fixed global batch (strong scaling); `value` above is weak scaling"}
+    if world > 1 and args.workload == "criteo":
+        # the other table layout on the same weak-scaling workload
+        alt = "replicated" if main["tables"] == "sharded" else "sharded"
+        r = measure(job, args, args.workload, primary, steps, 3, batch=args.batch, profile=True, tables=alt)
+        other_tables = {"tables": alt, "value": r["value"], "ms_per_step": r["ms_per_step"], "e2e": r["e2e"],
+                        "kernels": {k: v for k, v in r["kernels"].items() if k.startswith(("shard_", "dp_", "sort_", "sparse_"))}}
 
     # ---- the reference's own dataset shapes (N = 1 only; the data-parallel path is measured on the Criteo shape) ----
     workloads = {}
@@ -464,10 +483,13 @@ def run_ours(args):
             "dtype": DTYPE_NAME[primary], "dtype_note": DTYPE_NOTE[primary], "data": "synthetic",
             "config": cfg,
             "run": {"l2": main["l2"], "cuda_graph": main["cuda_graph"], "precision": primary,
-                    "parallelism": "dp%d (replicated tables, dense allreduce + touched-row allgather)" % world},
+                    "tables": main["tables"],
+                    "parallelism": ("dp%d, dense allreduce + " % world) + (
+                        "row-sharded tables: all-to-all of unique rows / gradient sums" if main["tables"] == "sharded" else
+                        "replicated tables: touched-row allgather" if world > 1 else "single GPU")},
             "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
             "roofline": main["roofline"], "kernels": main["kernels"], "cpu_baseline": cpu,
-            "modes": modes, "workloads": workloads, "strong": strong,
+            "modes": modes, "workloads": workloads, "strong": strong, "other_table_layout": other_tables,
             "wall_s_timed_region": main["wall_s_timed_region"], "final_loss": main["final_loss"],
         }
         print(json.dumps(line))

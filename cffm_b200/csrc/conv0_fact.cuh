@@ -42,10 +42,20 @@ struct F0Ctl {
 constexpr int F0_STAGE_BYTES = 8 * 32 * 32;   // per epilogue warp: [8 w][32 rows][16 channels] bf16
 constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
 static_assert(sizeof(F0Ctl) <= 256, "control block");
+// Split mode (CFFM_PREC_BF16X3): the A tile and every weight slab exist as hi and lo halves, Z is split into hi and
+// lo when it is converted (the two bf16 copies fill exactly the columns of the fp32 Z they are made from) and both
+// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of TWO
+// stages of (hi, lo) pairs (a q takes three times as long on the tensor pipe, so two are enough), and the epilogue
+// collects 8 channels instead of 16 (hi and lo tiles share a warp's staging space).
+constexpr int F0S_NST = 2;
+constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
+static_assert(F0S_SMEM <= 227 * 1024, "split-mode factorised forward exceeds the shared memory of an SM");
 
 struct Fwd0FactParams {
   CUtensorMap mapW;     // Wf0 viewed as [Q16*KA rows][nblk*64 cols] bf16, box (64, KA)
   CUtensorMap mapX;     // X1 as (q: Pp, row = b*16+h: B*16, w: 16), dense box (16, 32, 8) for the epilogue's TMA stores
+  CUtensorMap mapW2, mapX2;   // split mode: the lo halves (mapX / mapX2 then have box (8, 32, 8))
+  bf16* Xout_lo;
   int tma_store;        // 0: the tensor map could not be encoded, lanes store their sectors themselves
   const float* rows;    // outer rows [B][F][32]
   const float* bias;
@@ -84,7 +94,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 
 // Wf0[q][n = 2j+dw][k = 2i+dh] = Wf0T[q][k][n] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
 __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restrict__ pair_i, const int* __restrict__ pair_j, int P,
-                               int KA, int KP, bf16* __restrict__ out, bf16* __restrict__ outT) {
+                               int KA, int KP, bf16* __restrict__ out, bf16* __restrict__ outT, bf16* __restrict__ out_lo = nullptr,
+                               bf16* __restrict__ outT_lo = nullptr) {
   const int64_t total = 4ll * P * P;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(e % P);
@@ -95,16 +106,25 @@ __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restri
     const bf16 v = __float2bfloat16(W0[e]);
     out[((int64_t)q * KA + n) * KP + k] = v;
     if (outT) outT[((int64_t)q * KA + k) * KP + n] = v;   // transposed slabs (data gradient, conv0_dfact.cuh)
+    if (out_lo) {
+      const bf16 vl = __float2bfloat16(W0[e] - __bfloat162float(v));
+      out_lo[((int64_t)q * KA + n) * KP + k] = vl;
+      if (outT_lo) outT_lo[((int64_t)q * KA + k) * KP + n] = vl;
+    }
   }
 }
 
-template <int ACT>
+template <int ACT, bool SPLIT>
 __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_constant__ Fwd0FactParams prm) {
+  constexpr int NST = SPLIT ? F0S_NST : F0_NST;                         // slab ring depth
+  constexpr int SLAB_STAGE = (SPLIT ? 2 : 1) * F0_SLAB_BYTES;           // one stage: the slab (hi) [+ its lo half]
+  constexpr int AT_BYTES = (SPLIT ? 4 : 2) * A_STAGE_BYTES;             // A tile: [hi: nblk blocks][lo: nblk blocks]
+  constexpr int QG = SPLIT ? 8 : 16;                                    // channels an epilogue thread collects per store
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B]
-  uint8_t* sW = sAt + 2 * A_STAGE_BYTES;                 // ring of weight slabs
-  F0Ctl* ctl = reinterpret_cast<F0Ctl*>(sW + F0_NST * F0_SLAB_BYTES);
+  uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B] (split: hi at 0, lo at 2 * A_STAGE_BYTES)
+  uint8_t* sW = sAt + AT_BYTES;                          // ring of weight slabs
+  F0Ctl* ctl = reinterpret_cast<F0Ctl*>(sW + NST * SLAB_STAGE);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctl) + 256);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -114,9 +134,9 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
   const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t slab_bytes = (uint32_t)(nblk * KA * 128);
 
-  if (warp == 0 && lane == 0) prefetch_tmap(&prm.mapW);
+  if (warp == 0 && lane == 0) { prefetch_tmap(&prm.mapW); if (SPLIT) prefetch_tmap(&prm.mapW2); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < F0_NST; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
     for (int b = 0; b < F0_NZ; ++b) { mbar_init(&ctl->z_full[b], 1); mbar_init(&ctl->z_empty[b], 1); mbar_init(&ctl->zb_full[b], 4); }
     for (int b = 0; b < 2; ++b) { mbar_init(&ctl->d2_full[b], 1); mbar_init(&ctl->d2_empty[b], 8); }
     mbar_init(&ctl->a_ready, 8);
@@ -135,11 +155,13 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
       uint32_t n = 0;
       for (int t = 0; t < my_tiles; ++t)
         for (int q = 0; q < Q; ++q, ++n) {
-          const int s = n % F0_NST; const uint32_t ph = (n / F0_NST) & 1;
+          const int s = n % NST; const uint32_t ph = (n / NST) & 1;
           mbar_wait(&ctl->empty_b[s], ph ^ 1);
-          mbar_arrive_expect_tx(&ctl->full_b[s], slab_bytes);
-          for (int blk = 0; blk < nblk; ++blk)
-            tma_load_2d(sW + s * F0_SLAB_BYTES + blk * KA * 128, &prm.mapW, &ctl->full_b[s], blk * 64, q * KA);
+          mbar_arrive_expect_tx(&ctl->full_b[s], (SPLIT ? 2u : 1u) * slab_bytes);
+          for (int blk = 0; blk < nblk; ++blk) {
+            tma_load_2d(sW + s * SLAB_STAGE + blk * KA * 128, &prm.mapW, &ctl->full_b[s], blk * 64, q * KA);
+            if (SPLIT) tma_load_2d(sW + s * SLAB_STAGE + F0_SLAB_BYTES + blk * KA * 128, &prm.mapW2, &ctl->full_b[s], blk * 64, q * KA);
+          }
         }
     }
   } else if (warp == 1 || warp == 14) {
@@ -147,7 +169,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     // Two independent instruction streams coupled by mbarriers only.  All lanes run the loops (uniform control
     // flow); the MMAs and commits of one q sit inside ONE elect.sync region, which ptxas turns into
     // straight-line UTCHMMA issue (a lane == 0 test costs a 16-instruction per-thread loop around every
-    // tcgen05 instruction).  Slab stage = q & 3 and D buffer = q & 1 are compile-time (Q % 4 == 0); the Z
+    // tcgen05 instruction).  Slab stage = q % NST and D buffer = q & 1 are compile-time (Q % 4 == 0); the Z
     // buffer index runs modulo 3.
     const uint32_t at_addr = smem_u32(sAt);
     const int ksteps = KA / UMMA_K;
@@ -155,14 +177,16 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
 #pragma unroll
     for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
       adesc[k] = umma_desc_k_sw128(at_addr + (uint32_t)((k >> 2) * A_STAGE_BYTES)) + (uint64_t)((k & 3) * 2);
+    constexpr uint64_t A_LO = (uint64_t)((2 * A_STAGE_BYTES) >> 4);     // descriptor offset of the lo half of the A tile
     int zb = 0; uint32_t zph = 0;     // Z buffer of the current q and its phase
     if (warp == 1) {
       const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
-      uint64_t wdesc[F0_NST], wk[F0_KA_MAX / UMMA_K];
+      uint64_t wdesc[NST], wk[F0_KA_MAX / UMMA_K];
 #pragma unroll
-      for (int s = 0; s < F0_NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * F0_SLAB_BYTES));
+      for (int s = 0; s < NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * SLAB_STAGE));
 #pragma unroll
       for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
+      constexpr uint64_t W_LO = (uint64_t)(F0_SLAB_BYTES >> 4);
       uint32_t it = 0;
       for (int t = 0; t < my_tiles; ++t) {
         mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
@@ -170,15 +194,25 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
         for (int q = 0; q < Q; q += 4, ++it) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            mbar_wait(&ctl->full_b[u], it & 1);
+            // ring slot of q and its phase: 4 slots -> slot u, phase it & 1;  2 slots -> slot u & 1, phase (u >> 1) & 1
+            mbar_wait(&ctl->full_b[u % NST], NST == 4 ? (it & 1) : (uint32_t)((u >> 1) & 1));
             mbar_wait(&ctl->z_empty[zb], zph ^ 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t d1 = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
+              const uint64_t wd = wdesc[u % NST];
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-                if (k < ksteps) umma_bf16(d1, adesc[k], wdesc[u] + wk[k], idesc1, k != 0);
-              umma_commit(&ctl->empty_b[u]);
+                if (k < ksteps) umma_bf16(d1, adesc[k], wd + wk[k], idesc1, k != 0);
+              if constexpr (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) umma_bf16(d1, adesc[k] + A_LO, wd + wk[k], idesc1, true);            // lo * hi
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) umma_bf16(d1, adesc[k], wd + W_LO + wk[k], idesc1, true);            // hi * lo
+              }
+              umma_commit(&ctl->empty_b[u % NST]);
               umma_commit(&ctl->z_full[zb]);
             }
             __syncwarp();
@@ -188,6 +222,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
       }
     } else {
       const uint32_t idesc2 = umma_idesc_bf16(BM, 128);
+      const uint32_t z_lo = (uint32_t)(KA / 2);          // columns of the lo half of the converted Z
       for (int t = 0; t < my_tiles; ++t) {
         mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
         tc_fence_after();
@@ -203,6 +238,14 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
                 if (k < ksteps) umma_bf16_ts(d2, za + (uint32_t)(k * 8), adesc[k], idesc2, k != 0);
+              if constexpr (SPLIT) {
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) umma_bf16_ts(d2, za + z_lo + (uint32_t)(k * 8), adesc[k], idesc2, true);     // Z lo * A hi
+#pragma unroll
+                for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
+                  if (k < ksteps) umma_bf16_ts(d2, za + (uint32_t)(k * 8), adesc[k] + A_LO, idesc2, true);     // Z hi * A lo
+              }
               umma_commit(&ctl->z_empty[zb]);        // the Z buffer (fp32 and its bf16 overlay) is free again
               umma_commit(&ctl->d2_full[u & 1]);
             }
@@ -214,7 +257,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------------ converters: Z fp32 -> bf16, in place
-    // (the bf16 A operand of step 2 overwrites the first KA/2 columns of the fp32 Z it was made from)
+    // (the bf16 A operand of step 2 overwrites the first KA/2 columns of the fp32 Z it was made from; in split mode
+    // the lo half takes the other KA/2 columns)
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     int zb = 0; uint32_t zph = 0;
     for (int t = 0; t < my_tiles; ++t)
@@ -234,6 +278,11 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) pk[j] = pack2(v[c][2 * j], v[c][2 * j + 1]);
             tmem_st8(zaddr + (uint32_t)(c * 8), pk);
+            if constexpr (SPLIT) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = pack2_lo(v[c][2 * j], v[c][2 * j + 1]);
+              tmem_st8(zaddr + (uint32_t)(KA / 2 + c * 8), pk);
+            }
           }
         tmem_st_wait();
         tc_fence_before();
@@ -252,21 +301,24 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     const bool hi = (lane & 16) != 0;             // second sample of this warp: its block starts 16 columns later
     const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32 + grp * 8);
     float* xch = sbias + F0_BIAS_MAX;             // pooling sums of group 1, [2][128]
-    // staging tile of this warp for the TMA store (128-byte aligned, after xch)
+    // staging tile of this warp for the TMA store (128-byte aligned, after xch); split: hi tile, then lo tile
     uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xch + 2 * BM) + 127) & ~(uintptr_t)127) + ew * F0_STAGE_BYTES;
     auto build_a = [&](int tile) {
       const int b = tile * 8 + (r >> 4);
       const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
       for (int c = grp; c < KA / 8; c += 2) {     // 16-byte chunk c = fields 4c .. 4c+3
-        uint32_t wv[4];
+        uint32_t wv[4], wl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * c + e;
           float2 o = make_float2(0.f, 0.f);
           if (i < prm.F && b < prm.B) o = __ldg(reinterpret_cast<const float2*>(src + i * 32));
           wv[e] = pack2(o.x, o.y);
+          if (SPLIT) wl[e] = pack2_lo(o.x, o.y);
         }
         *reinterpret_cast<uint4*>(sAt + (c >> 3) * A_STAGE_BYTES + sw128_offset(r, c & 7)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        if (SPLIT)
+          *reinterpret_cast<uint4*>(sAt + (2 + (c >> 3)) * A_STAGE_BYTES + sw128_offset(r, c & 7)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -277,11 +329,12 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile * 8 + (r >> 4);
       float rowsum = 0.f;
-      for (int q0 = 0; q0 < Q; q0 += 16) {
-        uint32_t acc[8][8];
+      for (int q0 = 0; q0 < Q; q0 += QG) {
+        uint32_t acc[8][QG / 2];
+        uint32_t accl[SPLIT ? 8 : 1][QG / 2];
         float prev[8];
 #pragma unroll
-        for (int qq = 0; qq < 16; ++qq) {         // q & 1 == qq & 1, (q >> 1) & 1 == (qq >> 1) & 1
+        for (int qq = 0; qq < QG; ++qq) {         // q & 1 == qq & 1, (q >> 1) & 1 == (qq >> 1) & 1
           mbar_wait(&ctl->d2_full[qq & 1], (uint32_t)((qq >> 1) & 1));
           tc_fence_after();
           float lo[8], up[8];
@@ -296,28 +349,50 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           for (int w = 0; w < 8; ++w) {
             const float x = phi_f<ACT>((hi ? up[w] : lo[w]) + bq);
             rowsum += x;
-            if (qq & 1) acc[w][qq >> 1] = pack2(prev[w], x); else prev[w] = x;
+            if (qq & 1) {
+              acc[w][qq >> 1] = pack2(prev[w], x);
+              if constexpr (SPLIT) accl[w][qq >> 1] = pack2_lo(prev[w], x);
+            } else prev[w] = x;
           }
         }
         if (prm.tma_store) {
-          // 32 rows x 8 w x 16 channels of this warp -> staging tile -> one TMA store (rows beyond the batch are
+          // 32 rows x 8 w x QG channels of this warp -> staging tile -> one TMA store (rows beyond the batch are
           // clipped by the tensor map); the copy engine does the scattered 32-byte writes, not the LSU
           if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
           __syncwarp();
+          if constexpr (SPLIT) {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            uint4* d = reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 32);
-            d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
-            d[1] = make_uint4(acc[w][4], acc[w][5], acc[w][6], acc[w][7]);
+            for (int w = 0; w < 8; ++w) {
+              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+              *reinterpret_cast<uint4*>(stage + F0_STAGE_BYTES / 2 + (w * 32 + lane) * 16) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              uint4* d = reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 32);
+              d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+              d[1] = make_uint4(acc[w][QG / 2 - 4], acc[w][QG / 2 - 3], acc[w][QG / 2 - 2], acc[w][QG / 2 - 1]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
+          if (lane == 0) {
+            tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
+            if (SPLIT) tma_store_3d(&prm.mapX2, stage + F0_STAGE_BYTES / 2, q0, tile * BM + qd * 32, grp * 8);
+          }
         } else if (b < prm.B) {
-          bf16* dst = prm.Xout + (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
+          const int64_t off = (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
-            st_global_256(dst + (int64_t)w * prm.Pp, acc[w]);   // one full 32-byte sector per lane
+            if constexpr (SPLIT) {
+              *reinterpret_cast<uint4*>(prm.Xout + off + (int64_t)w * prm.Pp) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+              *reinterpret_cast<uint4*>(prm.Xout_lo + off + (int64_t)w * prm.Pp) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            } else {
+              uint32_t r8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r8[e] = acc[w][e % (QG / 2)];
+              st_global_256(prm.Xout + off + (int64_t)w * prm.Pp, r8);   // one full 32-byte sector per lane
+            }
           }
         }
       }

@@ -313,7 +313,9 @@ struct ConvDgradTC : KMajorA, KMajorB {
     const ConvDgradTC& p; int row, sub, lane; float dsp;
     uint8_t* stg;
     int64_t cbase[4]; bool cok[4];   // rows (lane>>2) + 8i of this warp's 32: element offset of this lane's 8 channels
-    uint4 mk[MAX_BN / 64][4];
+    // split mode: three times the MMA time per unit covers the drain, and the lo halves double its register need:
+    // the mask is then fetched chunk by chunk instead of for the whole unit ahead of the accumulator
+    uint4 mk[SPLIT ? 1 : MAX_BN / 64][4];
     __device__ Epilogue(const ConvDgradTC& p_, uint8_t* ex, int row_, int ew)
         : p(p_), row(row_), sub(ew >> 2), lane(threadIdx.x & 31), dsp(0.f), stg(ex + ew * 32 * STG) {}
     __device__ void begin(Unit) {}
@@ -333,13 +335,15 @@ struct ConvDgradTC : KMajorA, KMajorB {
         int b, h, w; p.g.pos(cok[i] ? m : 0, b, h, w);
         cbase[i] = (((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw) * p.g.Pp + pb + (lane & 3) * 8;
       }
+      if constexpr (!SPLIT) {
 #pragma unroll
-      for (int ci = 0; ci < MAX_BN / 64; ++ci) {
-        const int c0 = (2 * ci + sub) * 32;
-        if (c0 < p.g.BN) {
+        for (int ci = 0; ci < MAX_BN / 64; ++ci) {
+          const int c0 = (2 * ci + sub) * 32;
+          if (c0 < p.g.BN) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            mk[ci][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + cbase[i] + c0)) : make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < 4; ++i)
+              mk[ci][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + cbase[i] + c0)) : make_uint4(0u, 0u, 0u, 0u);
+          }
         }
       }
     }
@@ -348,6 +352,11 @@ struct ConvDgradTC : KMajorA, KMajorB {
     }
     __device__ __forceinline__ void chunk_i(Unit, int ci, int c0, const float (&v)[32]) {
       uint32_t o[16];
+      if constexpr (SPLIT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mk[0][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + cbase[i] + c0)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) o[j >> 1] = pack2((v[j] + dsp) * phi_scale<ACT>(), (v[j + 1] + dsp) * phi_scale<ACT>());
       stage_store(ci, c0, o, p.dYprev);
@@ -366,7 +375,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 d = *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * STG + (lane & 3) * 16);
-        const uint4 x = mk[ci][i];
+        const uint4 x = mk[SPLIT ? 0 : ci][i];
         d.x &= keep_bits(x.x); d.y &= keep_bits(x.y); d.z &= keep_bits(x.z); d.w &= keep_bits(x.w);
         if (cok[i]) *reinterpret_cast<uint4*>(dst + cbase[i] + c0) = d;
       }
@@ -842,6 +851,7 @@ struct TCState {
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
   float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
+  bf16* Wf0lo = nullptr;         // split mode: their lo halves
   bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
   float* df_bpart = nullptr;     // [tiles][4][Q16] column sums of dY0 collected by the factorised data gradient
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
@@ -898,14 +908,20 @@ int tc_alloc(Model* m, bool train) {
     const char* mf = getenv("CFFM_FACT_MIN_FIELDS");
     if (mb) st->fact_min_batch = atoi(mb);
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
-    // (split mode keeps layer 0 in the direct form: the factorised kernels round their intermediate Z / E to bf16)
-    if (!st->split && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
+    // (split mode: the forward kernel splits its intermediate Z into hi + lo as well; the factorised data and weight
+    // gradients round their intermediates to bf16 and are not used, layer 0's backward stays in the direct form)
+    if (2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
       st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0, n));
       CFFM_CUDA_OK(m, cudaMemset(st->Wf0, 0, sizeof(bf16) * (size_t)n));
       // channels Q16..Pp-1 of X1 are never written by that kernel
       CFFM_CUDA_OK(m, cudaMemset(st->X[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
+      if (st->split) {
+        TCTRY(tcmalloc(m, &st->Wf0lo, n));
+        CFFM_CUDA_OK(m, cudaMemset(st->Wf0lo, 0, sizeof(bf16) * (size_t)n));
+        CFFM_CUDA_OK(m, cudaMemset(st->Xlo[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
+      }
     }
   }
   if (train && !st->dY[0]) {
@@ -920,7 +936,7 @@ int tc_alloc(Model* m, bool train) {
     TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
     TCTRY(tcmalloc(m, &st->bg_partial, 2 * 148 * (int64_t)m->P));
     const char* d0 = getenv("CFFM_DGRAD0");
-    if (st->Wf0 && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
+    if (st->Wf0 && !st->split && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0T, n));
       CFFM_CUDA_OK(m, cudaMemset(st->Wf0T, 0, sizeof(bf16) * (size_t)n));
@@ -928,7 +944,7 @@ int tc_alloc(Model* m, bool train) {
       TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));
     }
     const char* w0 = getenv("CFFM_WGRAD0");
-    if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
+    if (st->Wf0 && !st->split && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
     {
       TCTRY(tcmalloc(m, &st->wf_part, (int64_t)W0_SPLIT_MAX * st->Q16 * st->KA * st->KA));
       TCTRY(tcmalloc(m, &st->A8, ((B + 7) / 8 * 8) * 16 * st->nblk * 64));
@@ -949,6 +965,7 @@ void tc_free(Model* m) {
   if (st->bg_partial) cudaFree(st->bg_partial);
   if (st->pool_part) cudaFree(st->pool_part);
   if (st->Wf0) cudaFree(st->Wf0);
+  if (st->Wf0lo) cudaFree(st->Wf0lo);
   if (st->Wf0T) cudaFree(st->Wf0T);
   if (st->pterm0) cudaFree(st->pterm0);
   if (st->df_bpart) cudaFree(st->df_bpart);
@@ -1001,30 +1018,33 @@ static int launch_tc(Model* m, const Pol& p, int units_hint, cudaStream_t s) {
 }
 #define TC_MAP_OK(m, ok) do { if (!(ok)) { (m)->err = "cuTensorMapEncodeTiled failed"; return CFFM_ERR_CUDA; } } while (0)
 
-template <int ACT>
+template <int ACT, bool SPLIT>
 static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream_t s) {
   Fwd0FactParams p;
-  memset(&p.mapW, 0, sizeof(p.mapW));
+  memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapW2, 0, sizeof(p.mapW2)); memset(&p.mapX2, 0, sizeof(p.mapX2));
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
-  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16, 32, 8) TMA stores
+  if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapW2, st->Wf0lo, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16 | 8, 32, 8) TMA stores
     const uint64_t dims[3] = {(uint64_t)st->Pp, (uint64_t)B * 16, 16};
     const uint64_t str[2] = {(uint64_t)16 * st->Pp * 2, (uint64_t)st->Pp * 2};
-    const uint32_t box[3] = {16, 32, 8};
+    const uint32_t box[3] = {SPLIT ? 8u : 16u, 32, 8};
     const char* e = getenv("CFFM_F0_TMASTORE");
     p.tma_store = !(e && !strcmp(e, "0")) && st->enc.encode_bf16(&p.mapX, st->X[1], 3, dims, str, box, false) ? 1 : 0;
-    if (!p.tma_store) memset(&p.mapX, 0, sizeof(p.mapX));
+    if (p.tma_store && SPLIT) p.tma_store = st->enc.encode_bf16(&p.mapX2, st->Xlo[1], 3, dims, str, box, false) ? 1 : 0;
+    if (!p.tma_store) { memset(&p.mapX, 0, sizeof(p.mapX)); memset(&p.mapX2, 0, sizeof(p.mapX2)); }
   }
-  p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1];
+  p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.Xout_lo = st->Xlo[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
+  constexpr int SMEM = SPLIT ? F0S_SMEM : F0_SMEM;
   static PerDeviceOnce attr_once;
   bool& attr_done = attr_once();
   if (!attr_done) {
-    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_fwd0_fact<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, F0_SMEM));
+    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_fwd0_fact<ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
-  k_fwd0_fact<ACT><<<grid, F0_THREADS, F0_SMEM, s>>>(p);
+  k_fwd0_fact<ACT, SPLIT><<<grid, F0_THREADS, SMEM, s>>>(p);
   m->launches++;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
@@ -1067,7 +1087,8 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
     m->launches++;
   }
   if (st->Wf0 && B >= st->fact_min_batch) {
-    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0, st->Wf0T);
+    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0, st->Wf0T,
+                                           st->Wf0lo, nullptr);
     m->launches++;
   }
   CFFM_CUDA_OK(m, cudaGetLastError());
@@ -1085,7 +1106,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
     CFFM_PROF(m, tag.c_str(), s);
     const int m_tiles = (g.M + BM - 1) / BM;
     if (l == 0 && st->Wf0 && B >= st->fact_min_batch) {
-      TCTRY(fwd0_fact_launch<ACT>(m, st, B, off, s));
+      TCTRY((fwd0_fact_launch<ACT, SPLIT>(m, st, B, off, s)));
     } else if (l == 0) {
       ConvFwdTC<ACT, true, SPLIT> p;
       // two accumulators (one per N tile of a unit) + four A stages share the 512 TMEM columns: N <= 192.

@@ -52,8 +52,8 @@ def gather_table(engine, name, dist=None, accum=False):
     if dist is None:
         import torch.distributed as dist
     local = engine.get_param(name, accum)
-    if not engine.shard:
-        return local
+    if not engine.shard or name not in engine.TABLES:
+        return local            # dense variables are replicated
     world = dist.get_world_size()
     parts = [None] * world
     dist.all_gather_object(parts, local)
