@@ -192,19 +192,23 @@ def executed_flops(spec, tag, B, precision):
     if not tag.startswith("conv_"):
         return None
     F, P = spec["F"], spec["F"] * (spec["F"] - 1) // 2
-    if precision == "bf16x3":
-        return 3.0 * algorithmic_work(spec, tag, B, 1)[1]
-    if precision != "bf16" or not tag.endswith("_l0") or 2 * F > 80 or F < 16 or B < 512:
-        return None
+    fact = tag.endswith("_l0") and 2 * F <= 80 and F >= 16 and B >= 512
     KA, Q16, tiles = (2 * F + 15) // 16 * 16, (P + 15) // 16 * 16, (B + 7) // 8
     per = 2.0 * 128 * KA * (KA + 128)          # one K=KA step + one K=128 (block-diagonal) step of a (tile, channel)
     table = {"conv_fwd_l0": per, "conv_dgrad_l0": 2 * per}
     if FACT_WGRAD:
         table["conv_wgrad_l0"] = 2.0 * 128 * 128 * (16 + KA)   # per-sample K=16 MMAs (N=16 each) + one K=128 step (N=KA)
+    if precision == "bf16x3":
+        if fact and tag in SPLIT_FACT:                          # factorised form with Z / E split into hi + lo
+            return 3.0 * tiles * Q16 * table[tag]
+        return 3.0 * algorithmic_work(spec, tag, B, 1)[1]
+    if precision != "bf16" or not fact:
+        return None
     return tiles * Q16 * table[tag] if tag in table else None
 
 
 FACT_WGRAD = True    # the layer-0 weight gradient runs in factorised form as well (conv0_wfact.cuh)
+SPLIT_FACT = ("conv_fwd_l0",)   # layer-0 kernels that run in factorised form in split (bf16x3) mode
 
 
 def ncu_traffic(spec, tag, B, precision):

@@ -46,7 +46,8 @@ def test_executed_flops_of_the_factorised_layer0_kernels():
     assert bench.executed_flops(spec, "conv_fwd_l1", 8192, "bf16") is None
     assert bench.executed_flops(spec, "conv_fwd_l0", 8192, "fp32") is None
     # split bf16: three MMAs per product, direct form on every layer
-    assert bench.executed_flops(spec, "conv_fwd_l0", 8192, "bf16x3") == 3 * algo
+    assert bench.executed_flops(spec, "conv_fwd_l0", 8192, "bf16x3") == 3 * fwd        # factorised, Z split
+    assert bench.executed_flops(spec, "conv_dgrad_l0", 8192, "bf16x3") == (3 * dgr if "conv_dgrad_l0" in bench.SPLIT_FACT else 3 * algo)
     assert bench.executed_flops(spec, "conv_dgrad_l2", 8192, "bf16x3") == 3 * bench.algorithmic_work(spec, "conv_dgrad_l2", 8192, 1)[1]
     assert bench.executed_flops(spec, "gather_outer", 8192, "bf16x3") is None
     assert bench.executed_flops(dict(spec, F=44), "conv_fwd_l0", 8192, "bf16") is None
