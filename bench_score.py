@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--batches", default="64,256,1024,4096,16384,65536")
     ap.add_argument("--dims", default="16,32,64")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--precisions", default="bf16,bf16x3,fp32")
     a = ap.parse_args()
     stream = torch.cuda.current_stream()
     for shape in a.shapes.split(","):
@@ -22,14 +23,15 @@ def main():
         F, M = len(cards), int(sum(cards))
         act = synth.WORKLOADS[shape]["activation"]
         for K in [int(k) for k in a.dims.split(",")]:
-            for prec in ("bf16", "fp32"):
-                if prec == "bf16" and K != 32:
-                    continue
+            for prec in a.precisions.split(","):
                 for B in [int(b) for b in a.batches.split(",")]:
                     P = F * (F - 1) // 2
                     S = sum((K >> (l + 1)) ** 2 for l in range(int(np.log2(K)) - 1))
                     flops = 2.0 * B * 4 * P * P * S
                     if prec == "fp32" and flops > 4e13:   # keep the SIMT cases to a few seconds
+                        continue
+                    # activations of a batch: B * S * Pp * 2 B (x2 in split mode): stay inside the GPU
+                    if B * S * ((P + 63) // 64 * 64) * (4 if prec == "bf16x3" else 2 if prec == "bf16" else 4) > 120e9:
                         continue
                     try:
                         eng = Engine(M, F, K, K, activation=act, max_batch=B, precision=prec, seed=1)

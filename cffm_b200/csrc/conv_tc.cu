@@ -78,7 +78,7 @@ struct SplitK {
 template <int ACT, bool L0, bool SPLIT = false>
 struct ConvFwdTC : KMajorA, KMajorB {
   static constexpr bool kSynthA = L0;
-  static constexpr int kStages = 4, kExtraBytes = L0 ? 24 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = L0 ? 8 : 4;
+  static constexpr int kStages = 4, kExtraBytes = L0 ? 28 * 1024 : 0, kATiles = 1, kAccBufs = 2, kEpiWarps = L0 ? 8 : 4;
   // layer 0: the synthesised cube slab goes to tensor memory (tcgen05.st) and the MMA reads A from there:
   // the kernel was bound by shared-memory bandwidth (STS of the slab + UMMA reads of A and B + LDS of the rows)
   // ... and every slab feeds two N tiles (kBPair): the producers, not the tensor pipe, bounded the kernel
@@ -129,13 +129,20 @@ struct ConvFwdTC : KMajorA, KMajorB {
   // table with one entry per pair of every stage: byte offsets of rows i and j (lo / hi 16 bits).
   // k = p*4 + dh*2 + dw: 16 consecutive pairs per 64-wide slab; no branches in the inner loop.
   struct SynthState {};
+  // A 128-row tile covers 128 / Ho^2 samples: one (K = 32: 256 positions per sample, K = 64: 1024) or two (K = 16: 64).
+  __device__ int samples_per_tile() const { const int s = BM >> (2 * g.lgHo); return s < 1 ? 1 : s; }
+  __device__ int sample_bytes() const { return (g.F + 1) * g.K * 4; }
   __device__ void synth_begin(Unit un, uint8_t* ex, int t, SynthState&) const {
-    float* o = reinterpret_cast<float*>(ex);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(ex + (g.F + 1) * g.K * 4);
-    const int b = (un.m_tile * BM) >> (2 * g.lgHo);
-    const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)b * g.F * g.K);
-    for (int e = t; e < g.F * g.K / 4; e += 256) reinterpret_cast<float4*>(o)[e] = __ldg(src + e);
-    for (int e = t; e < g.K / 4; e += 256) reinterpret_cast<float4*>(o + g.F * g.K)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int S = samples_per_tile();
+    uint32_t* tab = reinterpret_cast<uint32_t*>(ex + S * sample_bytes());
+    const int b0 = (un.m_tile * BM) >> (2 * g.lgHo);
+    for (int sl = 0; sl < S; ++sl) {
+      float* o = reinterpret_cast<float*>(ex + sl * sample_bytes());
+      const int b = b0 + sl;
+      const float4* src = reinterpret_cast<const float4*>(rows + (int64_t)(b < g.B ? b : 0) * g.F * g.K);
+      for (int e = t; e < g.F * g.K / 4; e += 256) reinterpret_cast<float4*>(o)[e] = b < g.B ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = t; e < g.K / 4; e += 256) reinterpret_cast<float4*>(o + g.F * g.K)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const uint32_t zero_row = (uint32_t)(g.F * g.K * 4);
     for (int e = t; e < g.Pp; e += 256)
       tab[e] = e < g.P ? ((uint32_t)(pair_i[e] * g.K * 4) | ((uint32_t)(pair_j[e] * g.K * 4) << 16)) : (zero_row | (zero_row << 16));
@@ -144,9 +151,9 @@ struct ConvFwdTC : KMajorA, KMajorB {
   __device__ void synth_regs(uint32_t (&pk)[16], Unit un, int kc_in, int t256, const uint8_t* ex) const {
     const int kc = sk.base(kc_in);
     const bool lo_part = sk.a_lo(kc_in);
-    const uint8_t* o = ex;
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(ex + (g.F + 1) * g.K * 4);
     const int t = t256 & 127, half = t256 >> 7;
+    const uint8_t* o = ex + (t >> (2 * g.lgHo)) * sample_bytes();      // this row's sample inside the tile
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(ex + samples_per_tile() * sample_bytes());
     const int m = un.m_tile * BM + t;
     const int h = (m >> g.lgHo) & (g.Ho - 1), w = m & (g.Ho - 1);
     const uint8_t* oh = o + 8 * h;
@@ -877,11 +884,22 @@ static int tcmalloc(Model* m, T** p, int64_t n) {
 }
 #define TCTRY(x) do { int _r = (x); if (_r != CFFM_OK) return _r; } while (0)
 
+// Scoring (forward only) runs on the tensor cores for outer_dims 16 / 32 / 64 and every activation (the sweep of
+// BASELINE.json configs[4]); training needs outer_dims == 32 and an activation whose derivative follows from the stored
+// post-activation (tc_train_supported).
 int tc_supported(Model* m) {
   if (!m->cfg.outer_conv) return CFFM_OK;
-  if (m->Ko != 32) { m->err = "precision bf16 needs outer_dims == 32 (other sizes run in fp32)"; return CFFM_ERR_UNSUPPORTED; }
-  if (m->cfg.activation == CFFM_ACT_GELU) { m->err = "precision bf16 does not support gelu yet (its derivative needs the pre-activation)"; return CFFM_ERR_UNSUPPORTED; }
-  if (m->F > 48) { m->err = "precision bf16 needs num_field <= 48"; return CFFM_ERR_UNSUPPORTED; }  // dgrad0 smem: 11*F*K*4 B
+  if (m->Ko != 16 && m->Ko != 32 && m->Ko != 64) { m->err = "tensor-core precisions need outer_dims 16, 32 or 64 (other sizes run in fp32)"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->F > 48) { m->err = "tensor-core precisions need num_field <= 48"; return CFFM_ERR_UNSUPPORTED; }  // dgrad0 smem: 11*F*K*4 B
+  // layer-0 forward: the rows of a tile's samples + the pair table share 14 KB of producer scratch
+  const int S = m->Ko == 16 ? 2 : 1, Pp = (m->P + 63) & ~63;
+  if (S * (m->F + 1) * m->Ko * 4 + Pp * 4 > 14 * 1024) { m->err = "tensor-core precisions: num_field too large for this outer_dims"; return CFFM_ERR_UNSUPPORTED; }
+  return CFFM_OK;
+}
+int tc_train_supported(Model* m) {
+  if (!m->cfg.outer_conv) return CFFM_OK;
+  if (m->Ko != 32) { m->err = "training in a tensor-core precision needs outer_dims == 32 (16 / 64: scoring only; train in fp32)"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->cfg.activation == CFFM_ACT_GELU) { m->err = "training in a tensor-core precision does not support gelu (its derivative needs the pre-activation); scoring does"; return CFFM_ERR_UNSUPPORTED; }
   return CFFM_OK;
 }
 
@@ -910,7 +928,7 @@ int tc_alloc(Model* m, bool train) {
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
     // (split mode: the forward kernel splits its intermediate Z into hi + lo as well; the factorised data and weight
     // gradients round their intermediates to bf16 and are not used, layer 0's backward stays in the direct form)
-    if (2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
+    if (m->Ko == 32 && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
       st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0, n));
@@ -925,6 +943,7 @@ int tc_alloc(Model* m, bool train) {
     }
   }
   if (train && !st->dY[0]) {
+    TCTRY(tc_train_supported(m));
     const int64_t B = m->max_batch, Pp = st->Pp;
     for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dY[l], B * H * H * Pp)); }
     if (st->split)

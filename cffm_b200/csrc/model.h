@@ -170,6 +170,7 @@ int run_backward_update(Model* m, const int32_t* ids_dev, const float* labels_de
 
 // tensor-core conv stack (CFFM_PREC_BF16), conv_tc.cu
 int tc_supported(Model* m);
+int tc_train_supported(Model* m);
 int tc_alloc(Model* m, bool train);
 void tc_free(Model* m);
 int tc_conv_forward(Model* m, int B, cudaStream_t s);

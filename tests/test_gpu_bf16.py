@@ -142,8 +142,16 @@ def test_bf16_training_tracks_fp32():
 
 
 def test_bf16_rejects_what_it_cannot_do():
+    """Scoring runs on the tensor cores for outer_dims 16 / 32 / 64 and every activation; TRAINING there needs
+    outer_dims == 32 and an activation whose derivative follows from the stored post-activation."""
     from cffm_b200 import Engine, CffmError
+    ids = np.zeros((4, 4), dtype=np.int32)
+    y = np.ones(4, dtype=np.float32)
+    for kw in (dict(inner_dims=16, outer_dims=16), dict(inner_dims=32, outer_dims=32, activation="gelu")):
+        eng = Engine(100, 4, max_batch=4, precision="bf16", **kw)
+        assert eng.forward(ids).shape == (4,)
+        with pytest.raises(CffmError):
+            eng.train_step(ids, y)
+        eng.close()
     with pytest.raises(CffmError):
-        Engine(100, 4, 16, 16, max_batch=4, precision="bf16")
-    with pytest.raises(CffmError):
-        Engine(100, 4, 32, 32, max_batch=4, precision="bf16", activation="gelu")
+        Engine(100, 4, 8, 8, max_batch=4, precision="bf16")

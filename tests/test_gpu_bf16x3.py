@@ -161,7 +161,47 @@ def test_reference_initialisers(name, precision, tol_out, tol_act):
     eng.close()
 
 
-def test_split_keeps_layer0_direct_and_rejects_like_bf16():
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("F,K,B,act", [(10, 16, 70, "selu"), (10, 64, 9, "relu"), (39, 16, 33, "relu"), (39, 64, 3, "elu"),
+                                       (6, 64, 20, "gelu"), (3, 16, 130, "prelu")])
+def test_scoring_on_tensor_cores_k16_k64(F, K, B, act, precision, tol):
+    """The scoring sweep of BASELINE.json configs[4] (outer_dims 16 / 32 / 64, Frappe and Criteo shapes) on tcgen05:
+    conv_depth = int(log2 K) (CFFM.py:373) gives 3 / 5 live layers, a 128-row tile holds two samples at K = 16 and an
+    eighth of one at K = 64.  Forward only: logits, pooled sums and stored activations against the fp64 oracle."""
+    from cffm_b200 import Engine
+    from oracle.cffm_ref import CFFMRef
+    M = 500
+    rng = np.random.default_rng(F * K)
+    eng = Engine(M, F, K, K, activation=act, max_batch=B, precision=precision, seed=3)
+    eng.set_param("feature_bias", rng.normal(0, 0.05, (M, 1)).astype(np.float32))
+    eng.set_param("outer_embeddings", rng.normal(0, 0.3, (M, K)).astype(np.float32))
+    P = F * (F - 1) // 2
+    depth = int(np.log2(K))
+    for l in range(depth):
+        eng.set_param("outer_layer_conv_weight_%d" % l, rng.normal(0, 1.0 / np.sqrt(4 * P), (2, 2, P, P)).astype(np.float32))
+    ref = CFFMRef(M, F, K, K, activation=act, dtype=torch.float64)
+    for k, v in eng.get_weights().items():
+        ref.params[k] = torch.from_numpy(v.astype(np.float64)).reshape(ref.params[k].shape)
+    ids = rng.integers(0, M, (B, F)).astype(np.int32)
+    out = eng.forward(ids)
+    want, inter = ref.forward(ids, return_intermediates=True)
+    for l in range(depth - 1):
+        got = eng.fetch("conv_%d" % l)
+        e = _rel(got, inter["conv_%d" % l].numpy())
+        assert e < 2 * tol, (F, K, precision, l, e)
+    assert _rel(eng.fetch("t1").reshape(B, -1), inter["t1"].numpy()) < tol
+    assert _rel(out, want.numpy()) < tol, (F, K, precision, _rel(out, want.numpy()))
+    # a slice scored alone equals the slice of the full batch (no cross-sample leakage through the shared tiles)
+    if B > 2:
+        assert np.array_equal(eng.forward(ids[1:B - 1]), out[1:B - 1])
+    eng.close()
+
+
+def test_split_rejects_like_bf16():
     from cffm_b200 import Engine, CffmError
     with pytest.raises(CffmError):
-        Engine(100, 4, 16, 16, max_batch=4, precision="bf16x3")
+        Engine(100, 4, 8, 8, max_batch=4, precision="bf16x3")
+    eng = Engine(100, 4, 16, 16, max_batch=4, precision="bf16x3")
+    with pytest.raises(CffmError):
+        eng.train_step(np.zeros((4, 4), dtype=np.int32), np.ones(4, dtype=np.float32))
+    eng.close()
