@@ -805,6 +805,70 @@ __global__ void k_colsum_bf16(const bf16* __restrict__ X, const bf16* __restrict
     partial[(int64_t)c * n + col] = t;
   }
 }
+// All layers' bias gradients in one launch pair (blockIdx.y = layer): the per-layer pair costs two launches per layer,
+// which is most of their time at the reference's dataset sizes.
+struct ColsumLayers {
+  const bf16* X[kMaxConv]; const bf16* Xlo[kMaxConv]; int64_t rows[kMaxConv]; int C[kMaxConv]; int64_t out_off[kMaxConv];
+  int n_layers, Pp, n; float* partial; int64_t partial_stride;
+};
+__global__ void k_colsum_bf16_layers(const ColsumLayers a) {
+  extern __shared__ float red[];               // [R][Pp]
+  const int l = blockIdx.y;
+  const int C = a.C[l];
+  const int c = blockIdx.x;
+  if (c >= C) return;
+  const bf16* __restrict__ X = a.X[l];
+  const bf16* __restrict__ Xlo = a.Xlo[l];
+  const int Pp = a.Pp;
+  const int CG = Pp >> 3;
+  const int R = blockDim.x / CG;
+  const int cg = threadIdx.x % CG, rl = threadIdx.x / CG;
+  const int64_t rows = a.rows[l];
+  const int64_t rpc = (rows + C - 1) / C;
+  const int64_t r0 = (int64_t)c * rpc;
+  const int64_t r1 = r0 + rpc < rows ? r0 + rpc : rows;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < R) {
+    for (int64_t r = r0 + rl; r < r1; r += R) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * Pp) + cg);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(wv[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(wv[j] & 0xFFFF0000u);
+      }
+      if (Xlo) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(Xlo + r * Pp) + cg);
+        const uint32_t uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(uv[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(uv[j] & 0xFFFF0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[rl * Pp + cg * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  float* partial = a.partial + (int64_t)l * a.partial_stride;
+  for (int col = threadIdx.x; col < a.n; col += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < R; ++q) t += red[q * Pp + col];
+    partial[(int64_t)c * a.n + col] = t;
+  }
+}
+__global__ void k_sum_chunks_layers(const ColsumLayers a, float* __restrict__ g) {
+  const int l = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  const float* partial = a.partial + (int64_t)l * a.partial_stride;
+  float s = 0.f;
+  for (int c = 0; c < a.C[l]; ++c) s += partial[(int64_t)c * a.n + j];
+  g[a.out_off[l] + j] = s;
+}
 __global__ void k_sum_chunks(const float* __restrict__ partial, int n, int C, float* __restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -953,7 +1017,7 @@ int tc_alloc(Model* m, bool train) {
     int max_split = (2 * 148 + tiles - 1) / tiles; if (max_split < 1) max_split = 1;
     st->wg_partial_floats = (int64_t)max_split * 4 * Pp * Pp;
     TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
-    TCTRY(tcmalloc(m, &st->bg_partial, 2 * 148 * (int64_t)m->P));
+    TCTRY(tcmalloc(m, &st->bg_partial, (int64_t)kMaxConv * 2 * 148 * (int64_t)m->P));
     const char* d0 = getenv("CFFM_DGRAD0");
     if (st->Wf0 && !st->split && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
@@ -1191,10 +1255,14 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
                                                             st->dYlo[l]);
     m->launches++;
   }
+  // Bias gradients d b_l = column sums of dY_l.  Big batches: per layer, right when dY_l has been written (it is still in
+  // L2).  Small batches (the reference's datasets): all layers in one launch pair after the loop -- at those sizes the
+  // eight launches cost more than the sums.
+  const bool colsum_late = (int64_t)B * (K / 2) * (K / 2) * Pp * 2 <= (int64_t)48 << 20;
   for (int l = m->n_live - 1; l >= 0; --l) {
     const Geom gm = make_geom(m, st, B, l);
     const int64_t rows = gm.M;
-    if (!(l == 0 && st->Wf0T && B >= st->fact_min_batch)) {  // bias gradient (layer 0, factorised: collected by k_dgrad0_fact)
+    if (!colsum_late && !(l == 0 && st->Wf0T && B >= st->fact_min_batch)) {  // (layer 0, factorised: collected by k_dgrad0_fact)
       CFFM_PROF(m, "colsum", s);
       const int C = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
       const int CG = Pp / 8;
@@ -1304,6 +1372,30 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         }
         TCTRY(launch_tc(m, p, ((gd.M + BM - 1) / BM) * gd.tiles_n, s));
       }
+    }
+  }
+  if (colsum_late) {
+    CFFM_PROF(m, "colsum", s);
+    ColsumLayers a;
+    memset(&a, 0, sizeof(a));
+    a.Pp = Pp; a.n = P; a.partial = st->bg_partial; a.partial_stride = (int64_t)2 * 148 * P;
+    int maxC = 1, nl = 0;
+    for (int l = 0; l < m->n_live; ++l) {
+      if (l == 0 && st->Wf0T && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
+      const int64_t rows = (int64_t)B * (K >> (l + 1)) * (K >> (l + 1));
+      a.X[nl] = st->dY[l]; a.Xlo[nl] = st->dYlo[l]; a.rows[nl] = rows;
+      a.C[nl] = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
+      a.out_off[nl] = m->lay.conv_b[l];
+      maxC = std::max(maxC, a.C[nl]);
+      ++nl;
+    }
+    a.n_layers = nl;
+    if (nl > 0) {
+      const int CG = Pp / 8;
+      int R = 512 / CG; if (R < 1) R = 1; if (R > 32) R = 32;
+      k_colsum_bf16_layers<<<dim3(maxC, nl), CG * R, sizeof(float) * R * Pp, s>>>(a);
+      k_sum_chunks_layers<<<dim3(ceil_div(P, 128), nl), 128, 0, s>>>(a, g);
+      m->launches += 2;
     }
   }
   return CFFM_OK;

@@ -27,6 +27,7 @@ constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int SEG_LT = 32;           // entries per chunk of the segmented reduction (one warp each: short chunks = more warps in flight)
 constexpr int SEG_SHORT_LIST = 32768; // up to this many entries: one warp per segment (k_seg_rows)
 constexpr int SEG_MAXC = 2;          // columns per lane and table (K <= 64)
+constexpr int SEG_LONG = 64;         // short lists: segments longer than this are summed by a whole block (k_seg_long)
 
 __global__ void k_rs_hist(const int32_t* __restrict__ keys, int n, int shift, int32_t* __restrict__ hist) {
   __shared__ int32_t h[256];
@@ -137,6 +138,90 @@ __global__ void k_seg_compact(const int32_t* __restrict__ sorted, int n, const i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Short lists (the reference's own datasets: Frappe 2 560 ids per step, ml-tag 3 072, Book-Crossing 3 072): the whole
+// sort + unique in ONE block instead of 3 launches per radix pass + 3 -- at these sizes the twelve launches cost more
+// than the work.  Same algorithm (stable LSD radix, 8 bits per pass, ranks by match_any), keys and positions ping-pong
+// in shared memory; then head flags -> scan -> seg_start / n_uniq.  Bit-identical output to the multi-kernel path.
+constexpr int SS_MAX = 4096, SS_THREADS = 1024;
+constexpr int SS_SMEM = (4 * SS_MAX + 256 + (SS_THREADS / 32) * 256 + 64) * 4;
+__global__ void __launch_bounds__(SS_THREADS, 1) k_small_sort_segments(const int32_t* __restrict__ ids, int n, int passes,
+                                                                       int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
+                                                                       int32_t* __restrict__ seg_start, int32_t* __restrict__ n_uniq) {
+  extern __shared__ int32_t ssm[];
+  int32_t* kA = ssm; int32_t* vA = kA + SS_MAX; int32_t* kB = vA + SS_MAX; int32_t* vB = kB + SS_MAX;
+  int32_t* base = vB + SS_MAX;                       // [256] next output slot of every digit
+  int32_t* wcnt = base + 256;                        // [32 warps][256]
+  int32_t* wtot = wcnt + (SS_THREADS / 32) * 256;    // [32] + running total
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n; i += SS_THREADS) { kA[i] = ids[i]; vA[i] = i; }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    if (tid < 256) base[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SS_THREADS) atomicAdd(&base[(kA[i] >> shift) & 255], 1);
+    __syncthreads();
+    if (warp == 0) {                                  // exclusive scan of the 256 digit counts: 8 per lane
+      int c[8], s = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = base[lane * 8 + j]; s += c[j]; }
+      int incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      int run = incl - s;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { base[lane * 8 + j] = run; run += c[j]; }
+    }
+    __syncthreads();
+    for (int r0 = 0; r0 < n; r0 += SS_THREADS) {      // stable scatter, one round of 1024 elements at a time
+      for (int e = tid; e < (SS_THREADS / 32) * 256; e += SS_THREADS) wcnt[e] = 0;
+      __syncthreads();
+      const int i = r0 + tid;
+      const bool ok = i < n;
+      const int32_t key = ok ? kA[i] : 0;
+      const int d = ok ? ((key >> shift) & 255) : 256;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      if (ok && rank == 0) wcnt[warp * 256 + d] = __popc(peers);
+      __syncthreads();
+      if (ok) {
+        int prior = 0;
+        for (int w8 = 0; w8 < warp; ++w8) prior += wcnt[w8 * 256 + d];
+        const int dst = base[d] + prior + rank;
+        kB[dst] = key; vB[dst] = vA[i];
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int add = 0;
+#pragma unroll 8
+        for (int w8 = 0; w8 < SS_THREADS / 32; ++w8) add += wcnt[w8 * 256 + tid];
+        base[tid] += add;
+      }
+      __syncthreads();
+    }
+    int32_t* t0 = kA; kA = kB; kB = t0; t0 = vA; vA = vB; vB = t0;
+  }
+  for (int i = tid; i < n; i += SS_THREADS) { keys_out[i] = kA[i]; vals_out[i] = vA[i]; }
+  // unique rows: head flags, block scan in rounds of 1024
+  if (tid == 0) wtot[32] = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < n; r0 += SS_THREADS) {
+    const int i = r0 + tid;
+    const bool head = i < n && (i == 0 || kA[i] != kA[i - 1]);
+    const unsigned mk = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) wtot[warp] = __popc(mk);
+    __syncthreads();
+    int prior = wtot[32];
+    for (int w8 = 0; w8 < warp; ++w8) prior += wtot[w8];
+    if (head) seg_start[prior + __popc(mk & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w8 = 0; w8 < SS_THREADS / 32; ++w8) t += wtot[w8]; wtot[32] += t; }
+    __syncthreads();
+  }
+  if (tid == 0) *n_uniq = wtot[32];
+}
+
 int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
   w->cap = cap;
   const int64_t ntiles = (cap + RS_TILE - 1) / RS_TILE;
@@ -177,6 +262,17 @@ int sparse_sort_segments(SparseWork* w, const int32_t* ids, int64_t n64, int fea
   int bits = 1;
   while (bits < 31 && (1ll << bits) < (long long)features_M) ++bits;
   const int passes = (bits + 7) / 8;
+  if (n <= SS_MAX) {
+    static PerDeviceOnce attr_once;
+    bool& attr_done = attr_once();
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(k_small_sort_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM) != cudaSuccess) return CFFM_ERR_CUDA;
+      attr_done = true;
+    }
+    k_small_sort_segments<<<1, SS_THREADS, SS_SMEM, s>>>(ids, n, passes, w->keys_out, w->vals_out, w->seg_start, w->n_uniq);
+    if (launches) *launches += 1;
+    return cudaGetLastError() == cudaSuccess ? CFFM_OK : CFFM_ERR_CUDA;
+  }
   const int ntiles = (n + RS_TILE - 1) / RS_TILE;
   int32_t* offs = reinterpret_cast<int32_t*>(w->cub_tmp);
   int32_t* tile_heads = offs + (size_t)ntiles * 256;
@@ -375,8 +471,9 @@ __global__ void k_seg_rows(const int32_t* __restrict__ sorted, const int32_t* __
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < U; sgm += nwarps) {
     const int start = seg_start[sgm], end = sgm + 1 < U ? seg_start[sgm + 1] : n;
+    if (end - start > SEG_LONG) continue;         // k_seg_long: one id that fills a good part of a batch
     SegAcc acc; seg_acc_zero(acc);
-    for (int tb = start; tb < end; tb += 8) {     // eight gradient rows in flight (one id can fill a whole batch)
+    for (int tb = start; tb < end; tb += 8) {     // eight gradient rows in flight
       SegAcc rows4[8];
       int pp[8];
 #pragma unroll
@@ -391,6 +488,48 @@ __global__ void k_seg_rows(const int32_t* __restrict__ sorted, const int32_t* __
           for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows4[u].v[j][c];
     }
     seg_acc_apply(acc, t, sorted[start], lane, opt, lr);
+  }
+}
+
+// Long segments of a short list (fields with two or three values put one id into most samples of a batch: Frappe has
+// three such fields): a block per segment, its eight warps sum eight consecutive pieces (order of appearance inside a
+// piece), warp 0 adds the pieces in order and applies.  A fixed function of the sorted list: deterministic.
+__global__ void k_seg_long(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start,
+                           const int32_t* __restrict__ n_uniq, int n, SparseTables t, int opt, float lr,
+                           const float* __restrict__ lr_dev) {
+  __shared__ float part[8][3 * SEG_MAXC * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int U = *n_uniq;
+  if (lr_dev) lr = *lr_dev;
+  for (int sgm = blockIdx.x; sgm < U; sgm += gridDim.x) {
+    const int start = seg_start[sgm], end = sgm + 1 < U ? seg_start[sgm + 1] : n;
+    if (end - start <= SEG_LONG) continue;        // block-uniform
+    const int piece = (((end - start + 7) >> 3) + 7) & ~7;
+    const int s0 = start + warp * piece, s1 = min(end, s0 + piece);
+    SegAcc acc; seg_acc_zero(acc);
+    for (int tb = s0; tb < s1; tb += 8) {
+      SegAcc rows8[8];
+      int pp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pp[u] = tb + u < s1 ? pos[tb + u] : 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { seg_acc_zero(rows8[u]); if (tb + u < s1) seg_acc_row(rows8[u], t, (int64_t)pp[u], lane); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows8[u].v[j][c];
+    }
+    seg_acc_store(acc, part[warp], lane);
+    __syncthreads();
+    if (warp == 0) {
+      SegAcc tot; seg_acc_zero(tot);
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) seg_acc_add(tot, part[w8], lane);
+      seg_acc_apply(tot, t, sorted[start], lane, opt, lr);
+    }
+    __syncthreads();
   }
 }
 
@@ -439,7 +578,9 @@ void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n,
   if (any_sparse && n <= SEG_SHORT_LIST) {
     int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
     k_seg_rows<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
-    if (launches) *launches += 1;
+    int lb = (int)((n + SEG_LONG - 1) / SEG_LONG); if (lb > 148 * 4) lb = 148 * 4;   // at most n / SEG_LONG long segments exist
+    k_seg_long<<<lb, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
+    if (launches) *launches += 2;
   } else if (any_sparse) {
     const int chunks = (int)((n + SEG_LT - 1) / SEG_LT);
     const int blocks = (chunks * 32 + 255) / 256;

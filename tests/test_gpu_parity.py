@@ -267,6 +267,62 @@ def test_sparse_adagrad_operator(n):
     assert np.allclose(got_w[uniq], w_want[uniq], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,M,K", [(1, 10, 4), (31, 7, 32), (1025, 3, 32), (2560, 5382, 32), (4096, 100000, 64), (4097, 100000, 16)])
+def test_sparse_update_short_lists(n, M, K):
+    """Lists up to 4096 ids (the reference's own datasets) take the one-block sort + unique and the per-segment kernels;
+    an id that fills a good part of the batch (Frappe has fields with two or three values) is summed by a whole block
+    (eight pieces, in order).  Unique rows bit exact, untouched rows bitwise unchanged, touched rows equal to the fp32
+    restatement of that summation order."""
+    from cffm_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    lr = 0.05
+    tab = rng.standard_normal((M, K)).astype(np.float32)
+    acc = np.full((M, K), 1e-8, dtype=np.float32)
+    ids = rng.integers(0, M, n).astype(np.int32)
+    grads = (rng.standard_normal((n, K)) * 0.1).astype(np.float32)
+    t_d, a_d = torch.from_numpy(tab).cuda(), torch.from_numpy(acc).cuda()
+    i_d, g_d = torch.from_numpy(ids).cuda(), torch.from_numpy(grads).cuda()
+    u_d = torch.zeros(n, dtype=torch.int32, device="cuda")
+    nu_d = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    rc = lib.cffm_op_sparse_adagrad_dev(C.c_void_p(t_d.data_ptr()), C.c_void_p(a_d.data_ptr()), M, K,
+                                        C.c_void_p(i_d.data_ptr()), C.c_void_p(g_d.data_ptr()), n, lr,
+                                        C.c_void_p(u_d.data_ptr()), C.c_void_p(nu_d.data_ptr()), C.c_void_p(0))
+    assert rc == 0
+    torch.cuda.synchronize()
+    uniq = np.unique(ids)
+    assert int(nu_d.item()) == len(uniq)
+    assert np.array_equal(u_d[: len(uniq)].cpu().numpy(), uniq)
+    order = np.argsort(ids, kind="stable")
+    G = np.zeros((M, K), dtype=np.float32)
+    for row in uniq:
+        src = order[ids[order] == row]                      # order of appearance
+        if len(src) <= 64 or n > 32768:
+            for p in src:
+                G[row] = G[row] + grads[p]
+        else:                                               # eight pieces of ((len + 7) / 8 rounded up to 8) entries
+            piece = (((len(src) + 7) >> 3) + 7) & ~7
+            parts = []
+            for w in range(8):
+                acc_p = np.zeros(K, dtype=np.float32)
+                for p in src[w * piece:min(len(src), (w + 1) * piece)]:      # order of appearance inside a piece
+                    acc_p = acc_p + grads[p]
+                parts.append(acc_p)
+            tot = np.zeros(K, dtype=np.float32)
+            for acc_p in parts:
+                tot = tot + acc_p
+            G[row] = tot
+    a_want = acc + G * G
+    w_want = tab - lr * G / np.sqrt(a_want)
+    got_w, got_a = t_d.cpu().numpy(), a_d.cpu().numpy()
+    mask = np.ones(M, dtype=bool); mask[uniq] = False
+    assert np.array_equal(got_w[mask], tab[mask]) and np.array_equal(got_a[mask], acc[mask])
+    assert np.allclose(got_a[uniq], a_want[uniq], rtol=2e-5, atol=1e-12)
+    assert np.allclose(got_w[uniq], w_want[uniq], rtol=0, atol=2e-5)
+
+
 def test_evaluate_matches_oracle():
     from cffm_b200 import Engine
     from oracle.cffm_ref import evaluate
