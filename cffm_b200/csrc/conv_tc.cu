@@ -728,8 +728,13 @@ struct ConvWgradTC : KMajorA, MNMajorB {
 // bf16 operand copies of the fp32 master filters W_l[(tap,p), q] (HWIO, CFFM.py:376-377):
 //   Wt[q][kk] (forward B operand) and Wd[kk][q] (data-gradient B operand), zero padded, with
 //   kk = tap*Pp + p for l >= 1 and kk = p*4 + tap for layer 0 (the order the cube is synthesised in).
-__global__ void k_prep_weights(const float* __restrict__ W, int P, int Pp, int l0, bf16* __restrict__ Wt, bf16* __restrict__ Wd,
-                               bf16* __restrict__ Wt_lo, bf16* __restrict__ Wd_lo) {
+struct PrepLayers { const float* W[kMaxConv]; bf16 *Wt[kMaxConv], *Wd[kMaxConv], *Wt_lo[kMaxConv], *Wd_lo[kMaxConv]; int l0[kMaxConv]; };
+__global__ void k_prep_weights(const PrepLayers a, int P, int Pp) {
+  const int ly = blockIdx.y;                                 // all layers in one launch
+  const float* __restrict__ W = a.W[ly];
+  bf16* __restrict__ Wt = a.Wt[ly]; bf16* __restrict__ Wd = a.Wd[ly];
+  bf16* __restrict__ Wt_lo = a.Wt_lo[ly]; bf16* __restrict__ Wd_lo = a.Wd_lo[ly];
+  const int l0 = a.l0[ly];
   const int64_t total = (int64_t)4 * Pp * Pp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int kk = (int)(e / Pp), q = (int)(e - (int64_t)kk * Pp);
@@ -1162,11 +1167,17 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   CFFM_PROF(m, "prep_weights_bf16", s);
   // layer 0: the direct kernels' bf16 copies are not needed when every layer-0 kernel of this call is the factorised one
   const bool fact0 = st->Wf0 && B >= st->fact_min_batch && (!st->dY[0] || (st->Wf0T && st->wf_part));
-  for (int l = fact0 ? 1 : 0; l < m->n_live; ++l) {
+  PrepLayers pa;
+  memset(&pa, 0, sizeof(pa));
+  int nl = 0;
+  for (int l = fact0 ? 1 : 0; l < m->n_live; ++l, ++nl) {
+    pa.W[nl] = m->dense_w + m->lay.conv_w[l]; pa.Wt[nl] = st->Wt[l]; pa.Wd[nl] = st->Wd[l];
+    pa.Wt_lo[nl] = st->Wtlo[l]; pa.Wd_lo[nl] = st->Wdlo[l]; pa.l0[nl] = l == 0 ? 1 : 0;
+  }
+  if (nl > 0) {
     const int64_t total = 4ll * st->Pp * st->Pp;
     int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    k_prep_weights<<<blocks, 256, 0, s>>>(m->dense_w + m->lay.conv_w[l], m->P, st->Pp, l == 0 ? 1 : 0, st->Wt[l], st->Wd[l],
-                                          st->Wtlo[l], st->Wdlo[l]);
+    k_prep_weights<<<dim3(blocks, nl), 256, 0, s>>>(pa, m->P, st->Pp);
     m->launches++;
   }
   if (st->Wf0 && B >= st->fact_min_batch) {

@@ -246,18 +246,37 @@ def test_sparse_adagrad_operator(n):
     uniq = np.unique(ids)
     assert int(nu_d.item()) == len(uniq)
     assert np.array_equal(u_d[: len(uniq)].cpu().numpy(), uniq)
-    # the kernel's summation order, restated.  Up to 32768 entries: a row's gradient rows in order of appearance.
+    # the kernel's summation order, restated.  Up to 32768 entries: a row's gradient rows in order of appearance (rows that
+    # appear more than 64 times: eight consecutive pieces, each in order of appearance, then the pieces in order).
     # Longer lists: the stably sorted list is cut into chunks of 32 entries; inside a chunk a row's gradient rows
     # are added in order of appearance, then the chunk pieces in chunk order (fp32)
     order = np.argsort(ids, kind="stable")
-    chunk_len = 32 if n > 32768 else n
-    pieces = {}
-    for t, src in enumerate(order):
-        key = (int(ids[src]), t // chunk_len)
-        pieces[key] = pieces.get(key, np.zeros(K, dtype=np.float32)) + grads[src]
     G = np.zeros((M, K), dtype=np.float32)
-    for (row, chunk) in sorted(pieces):
-        G[row] = G[row] + pieces[(row, chunk)]
+    if n > 32768:
+        pieces = {}
+        for t, src in enumerate(order):
+            key = (int(ids[src]), t // 32)
+            pieces[key] = pieces.get(key, np.zeros(K, dtype=np.float32)) + grads[src]
+        for (row, chunk) in sorted(pieces):
+            G[row] = G[row] + pieces[(row, chunk)]
+    else:
+        sorted_ids = ids[order]
+        bounds = np.flatnonzero(np.r_[True, sorted_ids[1:] != sorted_ids[:-1], True])
+        for a0, a1 in zip(bounds[:-1], bounds[1:]):
+            src = order[a0:a1]
+            row = int(sorted_ids[a0])
+            if len(src) <= 64:
+                for p in src:
+                    G[row] = G[row] + grads[p]
+            else:
+                piece = (((len(src) + 7) >> 3) + 7) & ~7
+                tot = np.zeros(K, dtype=np.float32)
+                for w in range(8):
+                    acc_p = np.zeros(K, dtype=np.float32)
+                    for p in src[w * piece:min(len(src), (w + 1) * piece)]:
+                        acc_p = acc_p + grads[p]
+                    tot = tot + acc_p
+                G[row] = tot
     a_want = acc + G * G
     w_want = tab - lr * G / np.sqrt(a_want)
     got_w, got_a = t_d.cpu().numpy(), a_d.cpu().numpy()
