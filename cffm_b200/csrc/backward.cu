@@ -741,8 +741,8 @@ int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, in
                              t.dense[j] = adam || l2; t.reg[j] = l2 ? m->cfg.lamda_att : 0.f; ++j; }
     t.tab[j] = m->fbias_tab; t.acc[j] = m->fbias_acc; t.acc2[j] = m->fbias_acc2; t.grads[j] = gbr; t.K[j] = 1; t.dense[j] = adam; ++j;
     if (opt == CFFM_OPT_SGD) for (int q = 0; q < 3; ++q) t.acc[q] = nullptr;
-    CFFM_PROF(m, "sparse_adagrad", s);
-    launch_sparse_update(&m->sw, t, n_upd, opt, m->cfg.lr, lr_dev, s, &m->launches);
+    { CFFM_PROF(m, "sparse_adagrad", s);
+      launch_sparse_update(&m->sw, t, n_upd, opt, m->cfg.lr, lr_dev, s, &m->launches); }
     // ---- dense update ----
     CFFM_PROF(m, "dense_adagrad", s);
     launch_dense_update(m->dense_w, opt == CFFM_OPT_SGD ? nullptr : m->dense_acc, m->dense_acc2, g, L.total, opt, m->cfg.lr, lr_dev, s);
