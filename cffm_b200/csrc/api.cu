@@ -631,7 +631,7 @@ extern "C" int cffm_op_sparse_adagrad_dev(float* table_dev, float* accum_dev, in
   SparseWork w;
   std::string err;
   cudaStreamSynchronize(s);
-  int r = sparse_work_alloc(&w, n, &err);
+  int r = sparse_work_alloc(&w, n, K, &err);
   if (r != CFFM_OK) { g_err = err; sparse_work_free(&w); return r; }
   r = sparse_sort_segments(&w, ids_dev, n, features_M, s, nullptr);
   if (r == CFFM_OK) {

@@ -514,7 +514,7 @@ int model_alloc_train(Model* m) {
   CFFM_CUDA_OK(m, cudaMemcpy(m->reduce_descs, d.data(), sizeof(ReduceDesc) * d.size(), cudaMemcpyHostToDevice));
   // sparse update scratch; under data parallelism the global batch is updated on every rank
   m->upd_cap = (int64_t)m->world * B * F;
-  if (sparse_work_alloc(&m->sw, m->upd_cap, &m->err) != CFFM_OK) return CFFM_ERR_NOMEM;
+  if (sparse_work_alloc(&m->sw, m->upd_cap, (m->cfg.inner_conv ? m->Ki : 0) + (m->cfg.outer_conv ? m->Ko : 0) + 1, &m->err) != CFFM_OK) return CFFM_ERR_NOMEM;
   if (m->world > 1 && !sharded(m)) {
     TRY(dmalloc(m, &m->all_ids, m->upd_cap));
     if (m->cfg.inner_conv) TRY(dmalloc(m, &m->all_g_inner, m->upd_cap * m->Ki));

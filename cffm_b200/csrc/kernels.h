@@ -23,10 +23,12 @@ struct SparseWork {
   uint8_t* flags = nullptr;       // ping-pong buffers of the radix sort
   void* cub_tmp = nullptr;        // digit offsets + per-tile segment-head counts
   float* pieces = nullptr;        // partial sums of segment pieces that cross chunk borders
+  float* gsum = nullptr;          // [cap * gcols] per-unique-row gradient sums (phase 1 of the update), table after table
   int32_t* chunk_flags = nullptr;
   size_t cub_tmp_bytes = 0;
 };
-int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err);
+// gcols = total columns of the tables whose gradient rows will be summed (Ki + Ko + 1)
+int sparse_work_alloc(SparseWork* w, int64_t cap, int gcols, std::string* err);
 void sparse_work_free(SparseWork* w);
 // sort ids, find segments; afterwards w->keys_out (sorted ids), w->vals_out (source positions),
 // w->seg_start (first sorted position of each unique row) and w->n_uniq are valid on the stream.
@@ -43,6 +45,8 @@ struct SparseTables {
   int32_t* rowmap = nullptr;                       // [M], -1 = untouched (dense passes only)
   int64_t M = 0;
 };
+// phase 1 only: sums per unique row into w->gsum (table j at cap * sum_{i<j} K_i, row stride K_j)
+void launch_segment_sums(const SparseWork* w, const SparseTables& t, int64_t n, cudaStream_t s, int64_t* launches);
 void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n, int opt, float lr, const float* lr_dev,
                           cudaStream_t s, int64_t* launches);
 void launch_dense_update(float* w, float* s1, float* s2, const float* g, int64_t n, int opt, float lr, const float* lr_dev,

@@ -38,7 +38,7 @@ struct ShardState {
   int32_t* h_counts = nullptr;    // pinned copy
   int32_t* ids_remap = nullptr;   // [cap] position of each id's row in the received list
   float *mini_inner = nullptr, *mini_outer = nullptr, *mini_bias = nullptr;   // [cap, K] rows received from the owners
-  float *u_inner = nullptr, *u_outer = nullptr, *u_bias = nullptr;            // [cap, K] gradient sums per unique row
+  // (the gradient sums per unique row of the backward exchange live in sw_req.gsum: phase 1 of update.cu)
   int32_t* req_rows = nullptr;    // [own_cap] local rows the ranks asked this rank for, rank-major
   float *x_inner = nullptr, *x_outer = nullptr, *x_bias = nullptr;            // [own_cap, K] rows out (forward) / gradient rows in (backward)
   std::vector<int64_t> send_cnt, send_off, recv_cnt, recv_off;               // of the last forward exchange
@@ -99,51 +99,6 @@ __global__ void k_gather_scalar(const float* __restrict__ tab, const int32_t* __
   if (i < n) out[i] = __ldg(tab + rows[i]);
 }
 
-// Gradient rows of one unique id summed in order of appearance (what unique + unsorted_segment_sum does on one
-// device, CFFM.py:523-524 [TF-1.14]); one warp per unique id, lane = column, four rows in flight.
-struct SegReduceArgs {
-  const int32_t *pos, *seg_start, *n_uniq; int n;
-  const float *g_inner, *g_outer, *g_bias; int Ki, Ko;
-  float *u_inner, *u_outer, *u_bias;
-};
-__global__ void k_seg_reduce_rows(const SegReduceArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int U = *a.n_uniq;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += nwarps) {
-    const int start = a.seg_start[u], end = u + 1 < U ? a.seg_start[u + 1] : a.n;
-    float si[2] = {0.f, 0.f}, so[2] = {0.f, 0.f}, sb = 0.f;
-    for (int tb = start; tb < end; tb += 4) {
-      int pp[4];
-      float vi[4][2], vo[4][2], vb[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pp[q] = tb + q < end ? a.pos[tb + q] : -1;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int k = lane + 32 * c;
-          vi[q][c] = (pp[q] >= 0 && a.g_inner && k < a.Ki) ? __ldg(a.g_inner + (int64_t)pp[q] * a.Ki + k) : 0.f;
-          vo[q][c] = (pp[q] >= 0 && a.g_outer && k < a.Ko) ? __ldg(a.g_outer + (int64_t)pp[q] * a.Ko + k) : 0.f;
-        }
-        vb[q] = (pp[q] >= 0 && lane == 0) ? __ldg(a.g_bias + pp[q]) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (pp[q] < 0) break;
-        si[0] += vi[q][0]; si[1] += vi[q][1]; so[0] += vo[q][0]; so[1] += vo[q][1]; sb += vb[q];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int k = lane + 32 * c;
-      if (a.u_inner && k < a.Ki) a.u_inner[(int64_t)u * a.Ki + k] = si[c];
-      if (a.u_outer && k < a.Ko) a.u_outer[(int64_t)u * a.Ko + k] = so[c];
-    }
-    if (lane == 0) a.u_bias[u] = sb;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 template <class T>
 static int smalloc(Model* m, T** p, int64_t n) {
@@ -167,7 +122,7 @@ static int shard_alloc(Model* m) {
   ss->own_cap = ss->cap * G;
   const int Ki = m->cfg.inner_conv ? m->Ki : 0, Ko = m->cfg.outer_conv ? m->Ko : 0;
   STRY(smalloc(m, &ss->keys, ss->cap));
-  if (sparse_work_alloc(&ss->sw_req, ss->cap, &m->err) != CFFM_OK) return CFFM_ERR_NOMEM;
+  if (sparse_work_alloc(&ss->sw_req, ss->cap, Ki + Ko + 1, &m->err) != CFFM_OK) return CFFM_ERR_NOMEM;
   STRY(smalloc(m, &ss->uniq_rows, ss->cap));
   STRY(smalloc(m, &ss->counts, G));
   STRY(smalloc(m, &ss->all_counts, (int64_t)G * G));
@@ -181,20 +136,11 @@ static int shard_alloc(Model* m) {
   return CFFM_OK;
 }
 
-static int shard_alloc_train(Model* m) {
-  ShardState* ss = m->shard;
-  if (ss->u_bias) return CFFM_OK;
-  if (m->cfg.inner_conv) STRY(smalloc(m, &ss->u_inner, ss->cap * m->Ki));
-  if (m->cfg.outer_conv) STRY(smalloc(m, &ss->u_outer, ss->cap * m->Ko));
-  STRY(smalloc(m, &ss->u_bias, ss->cap));
-  return CFFM_OK;
-}
-
 void shard_free(Model* m) {
   ShardState* ss = m->shard;
   if (!ss) return;
   void* p[] = {ss->keys, ss->uniq_rows, ss->counts, ss->all_counts, ss->ids_remap, ss->mini_inner, ss->mini_outer, ss->mini_bias,
-               ss->u_inner, ss->u_outer, ss->u_bias, ss->req_rows, ss->x_inner, ss->x_outer, ss->x_bias};
+               ss->req_rows, ss->x_inner, ss->x_outer, ss->x_bias};
   for (void* q : p) if (q) cudaFree(q);
   if (ss->h_counts) cudaFreeHost(ss->h_counts);
   sparse_work_free(&ss->sw_req);
@@ -283,24 +229,25 @@ int shard_forward_exchange(Model* m, const int32_t* ids, int64_t B, cudaStream_t
 int shard_backward_update(Model* m, int64_t B, cudaStream_t s) {
   ShardState* ss = m->shard;
   if (!ss) { m->err = "sharded tables: no forward exchange before the update"; return CFFM_ERR_INVALID; }
-  int r = shard_alloc_train(m); if (r != CFFM_OK) return r;
+  int r = CFFM_OK;
   const int n = (int)(B * m->F);
+  // per-unique-id sums on the requesting rank (phase 1 of the update, the summation order of a single device) ...
+  SparseTables tq;
+  int64_t goff[3] = {0, 0, 0};
   {
-    CFFM_PROF(m, "shard_grad_reduce", s);
-    SegReduceArgs a;
-    a.pos = ss->sw_req.vals_out; a.seg_start = ss->sw_req.seg_start; a.n_uniq = ss->sw_req.n_uniq; a.n = n;
-    a.g_inner = m->cfg.inner_conv ? m->g_inner_rows : nullptr; a.g_outer = m->cfg.outer_conv ? m->g_outer_rows : nullptr;
-    a.g_bias = m->g_bias_rows; a.Ki = m->Ki; a.Ko = m->Ko;
-    a.u_inner = ss->u_inner; a.u_outer = ss->u_outer; a.u_bias = ss->u_bias;
-    int blocks = (int)std::min<int64_t>(148 * 8, (ss->U * 32 + 255) / 256);
-    k_seg_reduce_rows<<<blocks, 256, 0, s>>>(a);
-    m->launches++;
+    int j = 0; int64_t off = 0;
+    if (m->cfg.inner_conv) { tq.tab[j] = ss->mini_inner; tq.grads[j] = m->g_inner_rows; tq.K[j] = m->Ki; goff[j] = off; off += ss->cap * m->Ki; ++j; }
+    if (m->cfg.outer_conv) { tq.tab[j] = ss->mini_outer; tq.grads[j] = m->g_outer_rows; tq.K[j] = m->Ko; goff[j] = off; off += ss->cap * m->Ko; ++j; }
+    tq.tab[j] = ss->mini_bias; tq.grads[j] = m->g_bias_rows; tq.K[j] = 1; goff[j] = off; ++j;
   }
-  {
+  { CFFM_PROF(m, "shard_grad_reduce", s);
+    launch_segment_sums(&ss->sw_req, tq, n, s, &m->launches); }
+  {  // ... and on to the owners
     CFFM_PROF(m, "shard_grad_a2a", s);
-    if (m->cfg.inner_conv) { r = all_to_all_rows(m, ss->u_inner, ss->x_inner, sizeof(float) * m->Ki, false, s); if (r != CFFM_OK) return r; }
-    if (m->cfg.outer_conv) { r = all_to_all_rows(m, ss->u_outer, ss->x_outer, sizeof(float) * m->Ko, false, s); if (r != CFFM_OK) return r; }
-    r = all_to_all_rows(m, ss->u_bias, ss->x_bias, sizeof(float), false, s); if (r != CFFM_OK) return r;
+    int j = 0;
+    if (m->cfg.inner_conv) { r = all_to_all_rows(m, ss->sw_req.gsum + goff[j], ss->x_inner, sizeof(float) * m->Ki, false, s); if (r != CFFM_OK) return r; ++j; }
+    if (m->cfg.outer_conv) { r = all_to_all_rows(m, ss->sw_req.gsum + goff[j], ss->x_outer, sizeof(float) * m->Ko, false, s); if (r != CFFM_OK) return r; ++j; }
+    r = all_to_all_rows(m, ss->sw_req.gsum + goff[j], ss->x_bias, sizeof(float), false, s); if (r != CFFM_OK) return r;
   }
   const int opt = m->cfg.optimizer;
   const bool adam = opt == CFFM_OPT_ADAM;

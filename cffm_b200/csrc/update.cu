@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SS_THREADS, 1) k_small_sort_segments(const int
   if (tid == 0) *n_uniq = wtot[32];
 }
 
-int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
+int sparse_work_alloc(SparseWork* w, int64_t cap, int gcols, std::string* err) {
   w->cap = cap;
   const int64_t ntiles = (cap + RS_TILE - 1) / RS_TILE;
   w->cub_tmp_bytes = sizeof(int32_t) * (size_t)(ntiles * 256 + ntiles + 16);   // digit offsets + per-tile head counts
@@ -240,6 +240,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
   {
     const int64_t chunks = (cap + SEG_LT - 1) / SEG_LT + 1;
     SW_ALLOC(w->pieces, sizeof(float) * chunks * 2 * 3 * SEG_MAXC * 32);
+    if (gcols > 0) SW_ALLOC(w->gsum, sizeof(float) * cap * gcols);   // per-unique-row sums of the three tables
     SW_ALLOC(w->chunk_flags, sizeof(int32_t) * chunks);
   }
 #undef SW_ALLOC
@@ -251,7 +252,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, std::string* err) {
 }
 
 void sparse_work_free(SparseWork* w) {
-  void* p[] = {w->keys_out, w->vals, w->vals_out, w->seg_start, w->n_uniq, w->flags, w->cub_tmp, w->pieces, w->chunk_flags};
+  void* p[] = {w->keys_out, w->vals, w->vals_out, w->seg_start, w->n_uniq, w->flags, w->cub_tmp, w->pieces, w->chunk_flags, w->gsum};
   for (void* q : p) if (q) cudaFree(q);
   *w = SparseWork();
 }
@@ -328,208 +329,253 @@ __device__ __forceinline__ float seg_sum(const float* __restrict__ grads, int K,
   return g;
 }
 
-// IndexedSlices de-duplication + SparseApply* on the touched rows only, as a chunked segmented
-// reduction: the sorted list is cut into chunks of SEG_LT entries, one warp per chunk adds the gradient
-// rows of every segment piece inside its chunk in order of appearance (lane = column).  A segment that
-// lies inside one chunk is applied at once; pieces of segments that cross chunk borders go to scratch and
-// k_seg_fixup adds them up, chunk after chunk, from the chunk the segment starts in.  Heavily duplicated
-// rows (one id in 20-95 % of a batch) no longer serialise on a single warp, and the
-// summation order is a fixed function of the sorted list: the update is deterministic.
-struct SegAcc { float v[3][SEG_MAXC]; };
+// IndexedSlices de-duplication + SparseApply* on the touched rows only, in two phases.
+//
+// Phase 1 (segment sums): the gradient rows of every unique id are added up -- in a summation order that is a fixed
+//   function of the sorted list, so the update is deterministic -- into a compact buffer G[segment][column] per table:
+//   * lists up to SEG_SHORT_LIST entries: one warp per segment, rows in order of appearance; a segment longer than
+//     SEG_LONG entries (fields with two or three values put one id into most samples of a batch) is cut into eight
+//     consecutive pieces summed by the eight warps of a block, then the pieces are added in order;
+//   * longer lists: the sorted list is cut into chunks of SEG_LT entries, one warp per chunk adds the rows of every
+//     segment piece inside its chunk in order of appearance; pieces of segments that cross chunk borders go to scratch
+//     and k_seg_sums_fixup adds them up, chunk after chunk, from the chunk the segment starts in.
+// Phase 2 (apply): one warp per unique row reads its sum and the row's variable / slots, applies the optimizer, writes
+//   back.  No warp ever waits for a table row while it still has gradient rows to add.
+// What the split buys: the positions and keys of a chunk come from one coalesced load (shuffled to the lanes that need
+// them), eight gradient rows are in flight per lane, and a chunk is 1 + 4 dependent memory round trips instead of 2 per
+// four entries plus 2 per segment end (ncu, Criteo shape: the single-phase kernel spent 70 % of its samples on
+// long_scoreboard with 8.6 % of DRAM bandwidth in use).
+template <int MAXC> struct SegAccT { float v[3][MAXC]; };
+struct GSums { float* g[3]; };   // per table: [segment][K]
 
-__device__ __forceinline__ void seg_acc_zero(SegAcc& a) {
+template <int MAXC> __device__ __forceinline__ void sa_zero(SegAccT<MAXC>& a) {
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int c = 0; c < SEG_MAXC; ++c) a.v[j][c] = 0.f;
+    for (int c = 0; c < MAXC; ++c) a.v[j][c] = 0.f;
 }
-__device__ __forceinline__ void seg_acc_row(SegAcc& a, const SparseTables& t, int64_t p, int lane) {
+template <int MAXC> __device__ __forceinline__ void sa_row(SegAccT<MAXC>& a, const SparseTables& t, int64_t p, int lane) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     if (!t.tab[j] || t.dense[j]) continue;
 #pragma unroll
-    for (int c = 0; c < SEG_MAXC; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
       const int k = lane + 32 * c;
-      if (k < t.K[j]) a.v[j][c] += __ldg(t.grads[j] + p * t.K[j] + k);
+      if (k < t.K[j]) a.v[j][c] = __ldg(t.grads[j] + p * t.K[j] + k);
     }
   }
 }
-__device__ __forceinline__ void seg_acc_apply(const SegAcc& a, const SparseTables& t, int64_t row, int lane, int opt, float lr) {
+template <int MAXC> __device__ __forceinline__ void sa_add(SegAccT<MAXC>& a, const SegAccT<MAXC>& b) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) a.v[j][c] += b.v[j][c];
+}
+template <int MAXC> __device__ __forceinline__ void sa_store_g(const SegAccT<MAXC>& a, const SparseTables& t, const GSums& G, int64_t sgm, int lane) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     if (!t.tab[j] || t.dense[j]) continue;
 #pragma unroll
-    for (int c = 0; c < SEG_MAXC; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
       const int k = lane + 32 * c;
-      if (k >= t.K[j]) continue;
-      const int64_t o = row * t.K[j] + k;
-      float w = t.tab[j][o], s1 = t.acc[j] ? t.acc[j][o] : 0.f, s2 = t.acc2[j] ? t.acc2[j][o] : 0.f;
-      opt_apply(opt, w, s1, s2, a.v[j][c], lr);
-      t.tab[j][o] = w;
-      if (t.acc[j]) t.acc[j][o] = s1;
-      if (t.acc2[j]) t.acc2[j][o] = s2;
+      if (k < t.K[j]) G.g[j][sgm * t.K[j] + k] = a.v[j][c];
     }
   }
 }
-// piece scratch: [chunk][slot 0/1][table][SEG_MAXC][32 lanes]
-__device__ __forceinline__ float* piece_ptr(float* pieces, int chunk, int slot) { return pieces + ((int64_t)chunk * 2 + slot) * (3 * SEG_MAXC * 32); }
-__device__ __forceinline__ void seg_acc_store(const SegAcc& a, float* p, int lane) {
+// piece scratch: [chunk][slot 0/1][table][MAXC][32 lanes]
+template <int MAXC> __device__ __forceinline__ float* piece_ptr(float* pieces, int chunk, int slot) { return pieces + ((int64_t)chunk * 2 + slot) * (3 * MAXC * 32); }
+template <int MAXC> __device__ __forceinline__ void sa_store_p(const SegAccT<MAXC>& a, float* p, int lane) {
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int c = 0; c < SEG_MAXC; ++c) p[(j * SEG_MAXC + c) * 32 + lane] = a.v[j][c];
+    for (int c = 0; c < MAXC; ++c) p[(j * MAXC + c) * 32 + lane] = a.v[j][c];
 }
-__device__ __forceinline__ void seg_acc_add(SegAcc& a, const float* p, int lane) {
+template <int MAXC> __device__ __forceinline__ void sa_add_p(SegAccT<MAXC>& a, const float* p, int lane) {
 #pragma unroll
   for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int c = 0; c < SEG_MAXC; ++c) a.v[j][c] += p[(j * SEG_MAXC + c) * 32 + lane];
+    for (int c = 0; c < MAXC; ++c) a.v[j][c] += p[(j * MAXC + c) * 32 + lane];
+}
+// index of the segment that contains sorted position t (warp-uniform)
+__device__ __forceinline__ int seg_of(const int32_t* __restrict__ seg_start, int U, int t) {
+  int lo = 0, hi = U - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_start[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 // flags[chunk]: bit0 = slot 1 holds the open tail piece of a segment that starts in this chunk;
 //               bit1 = slot 0 holds a middle piece (the segment covers the whole chunk and goes on)
-__global__ void k_seg_chunks(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, int n, SparseTables t, int opt,
-                             float lr, const float* __restrict__ lr_dev, float* __restrict__ pieces, int32_t* __restrict__ flags) {
+template <int MAXC>
+__global__ void k_seg_sums_chunks(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start,
+                                  const int32_t* __restrict__ n_uniq, int n, SparseTables t, GSums G, float* __restrict__ pieces,
+                                  int32_t* __restrict__ flags) {
+  static_assert(SEG_LT == 32, "one entry per lane");
   const int lane = threadIdx.x & 31;
   const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int t0 = chunk * SEG_LT;
   if (t0 >= n) return;
-  if (lr_dev) lr = *lr_dev;
   const int t1 = min(n, t0 + SEG_LT);
+  // one coalesced load brings the chunk's positions and keys; the lanes get them by shuffle
+  const int my_pos = t0 + lane < t1 ? pos[t0 + lane] : 0;
+  const int my_key = t0 + lane < t1 ? sorted[t0 + lane] : -1;
+  const int key_after = t0 + SEG_LT < n ? sorted[t0 + SEG_LT] : -1;
   const bool head_open = t0 > 0 && sorted[t0 - 1] == sorted[t0];
+  int sgm = seg_of(seg_start, *n_uniq, t0);
   int fl = 0;
-  SegAcc acc; seg_acc_zero(acc);
+  SegAccT<MAXC> acc; sa_zero(acc);
   bool first_piece = true;
-  int key = sorted[t0];
-  // four entries per trip: their positions, keys and gradient rows are loaded before any is added
-  for (int tb = t0; tb < t1; tb += 4) {
-    int pp[4], kk[5];
-    SegAcc rows4[4];
+  for (int tb = 0; tb < SEG_LT; tb += 8) {
+    if (t0 + tb >= t1) break;
+    SegAccT<MAXC> rows8[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int tt = tb + u;
-      pp[u] = tt < t1 ? pos[tt] : 0;
-      kk[u] = tt < n ? sorted[tt] : -1;
+    for (int u = 0; u < 8; ++u) {
+      const int p = __shfl_sync(0xffffffffu, my_pos, tb + u);
+      sa_zero(rows8[u]);
+      if (t0 + tb + u < t1) sa_row(rows8[u], t, (int64_t)p, lane);
     }
-    kk[4] = tb + 4 < n ? sorted[tb + 4] : -1;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { seg_acc_zero(rows4[u]); if (tb + u < t1) seg_acc_row(rows4[u], t, (int64_t)pp[u], lane); }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int tt = tb + u;
-      if (tt >= t1) break;
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows4[u].v[j][c];
-      const bool last_in_chunk = tt + 1 == t1;
-      const int nxt = kk[u + 1];
-      if (last_in_chunk || nxt != key) {
-        const bool closes = nxt != key;                          // the segment ends with this entry
-        const bool started_inside = !(first_piece && head_open);
-        if (started_inside && closes) seg_acc_apply(acc, t, key, lane, opt, lr);
-        else if (!started_inside && closes) seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane);
-        else if (started_inside && !closes) { seg_acc_store(acc, piece_ptr(pieces, chunk, 1), lane); fl |= 1; }
-        else { seg_acc_store(acc, piece_ptr(pieces, chunk, 0), lane); fl |= 2; }
-        seg_acc_zero(acc);
-        first_piece = false;
-        key = nxt;
+    for (int u = 0; u < 8; ++u) {
+      const int key = __shfl_sync(0xffffffffu, my_key, tb + u);
+      const int nxt_in = __shfl_sync(0xffffffffu, my_key, (tb + u + 1) & 31);
+      const int tt = t0 + tb + u;
+      if (tt < t1) {                                           // warp-uniform
+        const int nxt = tb + u + 1 < SEG_LT ? nxt_in : key_after;
+        sa_add(acc, rows8[u]);
+        const bool last_in_chunk = tt + 1 == t1;
+        if (last_in_chunk || nxt != key) {
+          const bool closes = nxt != key;                        // the segment ends with this entry
+          const bool started_inside = !(first_piece && head_open);
+          if (started_inside && closes) sa_store_g(acc, t, G, (int64_t)sgm, lane);
+          else if (!started_inside && closes) sa_store_p(acc, piece_ptr<MAXC>(pieces, chunk, 0), lane);
+          else if (started_inside && !closes) { sa_store_p(acc, piece_ptr<MAXC>(pieces, chunk, 1), lane); fl |= 1; }
+          else { sa_store_p(acc, piece_ptr<MAXC>(pieces, chunk, 0), lane); fl |= 2; }
+          sa_zero(acc);
+          first_piece = false;
+          if (closes) ++sgm;
+        }
       }
     }
   }
   if (lane == 0) flags[chunk] = fl;
 }
 
-__global__ void k_seg_fixup(const int32_t* __restrict__ sorted, int n, SparseTables t, int opt, float lr,
-                            const float* __restrict__ lr_dev, const float* __restrict__ pieces, const int32_t* __restrict__ flags) {
+template <int MAXC>
+__global__ void k_seg_sums_fixup(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, SparseTables t, GSums G,
+                                 const float* __restrict__ pieces, const int32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int t0 = chunk * SEG_LT;
   if (t0 >= n) return;
   if (!(flags[chunk] & 1)) return;                              // no segment starts here and runs on
-  if (lr_dev) lr = *lr_dev;
   const int t1 = min(n, t0 + SEG_LT);
-  const int key = sorted[t1 - 1];
-  SegAcc acc; seg_acc_zero(acc);
-  seg_acc_add(acc, piece_ptr(const_cast<float*>(pieces), chunk, 1), lane);
+  SegAccT<MAXC> acc; sa_zero(acc);
+  sa_add_p(acc, piece_ptr<MAXC>(const_cast<float*>(pieces), chunk, 1), lane);
   for (int cc = chunk + 1;; ++cc) {                            // the pieces of the following chunks, in order
-    seg_acc_add(acc, piece_ptr(const_cast<float*>(pieces), cc, 0), lane);
+    sa_add_p(acc, piece_ptr<MAXC>(const_cast<float*>(pieces), cc, 0), lane);
     if (!(flags[cc] & 2)) break;                               // a first piece: the segment ends inside chunk cc
   }
-  seg_acc_apply(acc, t, key, lane, opt, lr);
+  sa_store_g(acc, t, G, (int64_t)seg_of(seg_start, *n_uniq, t1 - 1), lane);
 }
 
-// Short lists (the small workloads: a few thousand entries): one warp per segment, all segments in parallel.  The
-// chunked kernels above walk 128 entries per warp and apply their segments one after the other, which costs
-// ~100 us of pure latency when there are only a few dozen chunks.  Rows are added in order of appearance.
-__global__ void k_seg_rows(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start,
-                           const int32_t* __restrict__ n_uniq, int n, SparseTables t, int opt, float lr,
-                           const float* __restrict__ lr_dev) {
+// Short lists (the small workloads: a few thousand entries): one warp per segment, all segments in parallel; rows are
+// added in order of appearance.  Positions come 32 at a time from one coalesced load.
+template <int MAXC>
+__global__ void k_seg_sums_rows(const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq,
+                                int n, SparseTables t, GSums G) {
   const int lane = threadIdx.x & 31;
   const int U = *n_uniq;
-  if (lr_dev) lr = *lr_dev;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < U; sgm += nwarps) {
     const int start = seg_start[sgm], end = sgm + 1 < U ? seg_start[sgm + 1] : n;
-    if (end - start > SEG_LONG) continue;         // k_seg_long: one id that fills a good part of a batch
-    SegAcc acc; seg_acc_zero(acc);
-    for (int tb = start; tb < end; tb += 8) {     // eight gradient rows in flight
-      SegAcc rows4[8];
-      int pp[8];
+    if (end - start > SEG_LONG) continue;         // k_seg_sums_long: one id that fills a good part of a batch
+    SegAccT<MAXC> acc; sa_zero(acc);
+    for (int b0 = start; b0 < end; b0 += 32) {
+      const int my_pos = b0 + lane < end ? pos[b0 + lane] : 0;
+      for (int tb = 0; tb < 32 && b0 + tb < end; tb += 8) {
+        SegAccT<MAXC> rows8[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) pp[u] = tb + u < end ? pos[tb + u] : 0;
+        for (int u = 0; u < 8; ++u) {
+          const int p = __shfl_sync(0xffffffffu, my_pos, tb + u);
+          sa_zero(rows8[u]);
+          if (b0 + tb + u < end) sa_row(rows8[u], t, (int64_t)p, lane);
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { seg_acc_zero(rows4[u]); if (tb + u < end) seg_acc_row(rows4[u], t, (int64_t)pp[u], lane); }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows4[u].v[j][c];
+        for (int u = 0; u < 8; ++u) sa_add(acc, rows8[u]);       // (rows beyond the segment are zero)
+      }
     }
-    seg_acc_apply(acc, t, sorted[start], lane, opt, lr);
+    sa_store_g(acc, t, G, (int64_t)sgm, lane);
   }
 }
 
-// Long segments of a short list (fields with two or three values put one id into most samples of a batch: Frappe has
-// three such fields): a block per segment, its eight warps sum eight consecutive pieces (order of appearance inside a
-// piece), warp 0 adds the pieces in order and applies.  A fixed function of the sorted list: deterministic.
-__global__ void k_seg_long(const int32_t* __restrict__ sorted, const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start,
-                           const int32_t* __restrict__ n_uniq, int n, SparseTables t, int opt, float lr,
-                           const float* __restrict__ lr_dev) {
-  __shared__ float part[8][3 * SEG_MAXC * 32];
+// Long segments of a short list: a block per segment, its eight warps sum eight consecutive pieces (order of
+// appearance inside a piece), warp 0 adds the pieces in order.
+template <int MAXC>
+__global__ void k_seg_sums_long(const int32_t* __restrict__ pos, const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq,
+                                int n, SparseTables t, GSums G) {
+  __shared__ float part[8][3 * MAXC * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int U = *n_uniq;
-  if (lr_dev) lr = *lr_dev;
   for (int sgm = blockIdx.x; sgm < U; sgm += gridDim.x) {
     const int start = seg_start[sgm], end = sgm + 1 < U ? seg_start[sgm + 1] : n;
     if (end - start <= SEG_LONG) continue;        // block-uniform
     const int piece = (((end - start + 7) >> 3) + 7) & ~7;
     const int s0 = start + warp * piece, s1 = min(end, s0 + piece);
-    SegAcc acc; seg_acc_zero(acc);
-    for (int tb = s0; tb < s1; tb += 8) {
-      SegAcc rows8[8];
-      int pp[8];
+    SegAccT<MAXC> acc; sa_zero(acc);
+    for (int b0 = s0; b0 < s1; b0 += 32) {
+      const int my_pos = b0 + lane < s1 ? pos[b0 + lane] : 0;
+      for (int tb = 0; tb < 32 && b0 + tb < s1; tb += 8) {
+        SegAccT<MAXC> rows8[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) pp[u] = tb + u < s1 ? pos[tb + u] : 0;
+        for (int u = 0; u < 8; ++u) {
+          const int p = __shfl_sync(0xffffffffu, my_pos, tb + u);
+          sa_zero(rows8[u]);
+          if (b0 + tb + u < s1) sa_row(rows8[u], t, (int64_t)p, lane);
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { seg_acc_zero(rows8[u]); if (tb + u < s1) seg_acc_row(rows8[u], t, (int64_t)pp[u], lane); }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int c = 0; c < SEG_MAXC; ++c) acc.v[j][c] += rows8[u].v[j][c];
+        for (int u = 0; u < 8; ++u) sa_add(acc, rows8[u]);
+      }
     }
-    seg_acc_store(acc, part[warp], lane);
+    sa_store_p(acc, part[warp], lane);
     __syncthreads();
     if (warp == 0) {
-      SegAcc tot; seg_acc_zero(tot);
+      SegAccT<MAXC> tot; sa_zero(tot);
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) seg_acc_add(tot, part[w8], lane);
-      seg_acc_apply(tot, t, sorted[start], lane, opt, lr);
+      for (int w8 = 0; w8 < 8; ++w8) sa_add_p(tot, part[w8], lane);
+      sa_store_g(tot, t, G, (int64_t)sgm, lane);
     }
     __syncthreads();
+  }
+}
+
+// Phase 2: SparseApply* on the unique rows, one warp per row.
+template <int MAXC>
+__global__ void k_apply_rows(const int32_t* __restrict__ sorted, const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq,
+                             SparseTables t, GSums G, int opt, float lr, const float* __restrict__ lr_dev) {
+  const int lane = threadIdx.x & 31;
+  const int U = *n_uniq;
+  if (lr_dev) lr = *lr_dev;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int sgm = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sgm < U; sgm += nwarps) {
+    const int64_t row = sorted[seg_start[sgm]];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (!t.tab[j] || t.dense[j]) continue;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int k = lane + 32 * c;
+        if (k >= t.K[j]) continue;
+        const int64_t o = row * t.K[j] + k;
+        const float g = G.g[j][(int64_t)sgm * t.K[j] + k];
+        float w = t.tab[j][o], s1 = t.acc[j] ? t.acc[j][o] : 0.f, s2 = t.acc2[j] ? t.acc2[j][o] : 0.f;
+        opt_apply(opt, w, s1, s2, g, lr);
+        t.tab[j][o] = w;
+        if (t.acc[j]) t.acc[j][o] = s1;
+        if (t.acc2[j]) t.acc2[j][o] = s2;
+      }
+    }
   }
 }
 
@@ -570,23 +616,53 @@ __global__ void k_table_dense_update(float* __restrict__ tab, float* __restrict_
   }
 }
 
+static GSums gsums_of(const SparseWork* w, const SparseTables& t) {
+  GSums G; int64_t off = 0;
+  for (int j = 0; j < 3; ++j) { G.g[j] = w->gsum ? w->gsum + off : nullptr; off += w->cap * (int64_t)(t.tab[j] ? t.K[j] : 0); }
+  return G;
+}
+
+// Phase 1 alone: per-unique-row sums of the gradient rows into w->gsum (table j at offset cap * sum_{i<j} K_i, row stride
+// K_j, one row per segment of the sorted list).  Also used by the row-sharded exchange, which ships these sums.
+template <int MAXC>
+static void segment_sums_t(const SparseWork* w, const SparseTables& t, int64_t n, cudaStream_t s, int64_t* launches) {
+  const GSums G = gsums_of(w, t);
+  if (n <= SEG_SHORT_LIST) {
+    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+    k_seg_sums_rows<MAXC><<<blocks, 256, 0, s>>>(w->vals_out, w->seg_start, w->n_uniq, (int)n, t, G);
+    int lb = (int)((n + SEG_LONG - 1) / SEG_LONG); if (lb > 148 * 4) lb = 148 * 4;   // at most n / SEG_LONG long segments exist
+    if (n > SEG_LONG) { k_seg_sums_long<MAXC><<<lb, 256, 0, s>>>(w->vals_out, w->seg_start, w->n_uniq, (int)n, t, G); if (launches) *launches += 1; }
+    if (launches) *launches += 1;
+  } else {
+    const int chunks = (int)((n + SEG_LT - 1) / SEG_LT);
+    const int blocks = (chunks * 32 + 255) / 256;
+    k_seg_sums_chunks<MAXC><<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, G, w->pieces, w->chunk_flags);
+    k_seg_sums_fixup<MAXC><<<blocks, 256, 0, s>>>(w->seg_start, w->n_uniq, (int)n, t, G, w->pieces, w->chunk_flags);
+    if (launches) *launches += 2;
+  }
+}
+static int maxc_of(const SparseTables& t) {
+  int k = 1;
+  for (int j = 0; j < 3; ++j) if (t.tab[j] && !t.dense[j] && t.K[j] > k) k = t.K[j];
+  return k > 32 ? 2 : 1;
+}
+void launch_segment_sums(const SparseWork* w, const SparseTables& t, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n <= 0) return;
+  if (maxc_of(t) == 2) segment_sums_t<2>(w, t, n, s, launches); else segment_sums_t<1>(w, t, n, s, launches);
+}
+
 void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n, int opt, float lr, const float* lr_dev,
                           cudaStream_t s, int64_t* launches) {
   if (n <= 0) return;
   bool any_sparse = false, any_dense = false;
   for (int j = 0; j < 3; ++j) if (t.tab[j]) { if (t.dense[j]) any_dense = true; else any_sparse = true; }
-  if (any_sparse && n <= SEG_SHORT_LIST) {
-    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    k_seg_rows<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
-    int lb = (int)((n + SEG_LONG - 1) / SEG_LONG); if (lb > 148 * 4) lb = 148 * 4;   // at most n / SEG_LONG long segments exist
-    k_seg_long<<<lb, 256, 0, s>>>(w->keys_out, w->vals_out, w->seg_start, w->n_uniq, (int)n, t, opt, lr, lr_dev);
-    if (launches) *launches += 2;
-  } else if (any_sparse) {
-    const int chunks = (int)((n + SEG_LT - 1) / SEG_LT);
-    const int blocks = (chunks * 32 + 255) / 256;
-    k_seg_chunks<<<blocks, 256, 0, s>>>(w->keys_out, w->vals_out, (int)n, t, opt, lr, lr_dev, w->pieces, w->chunk_flags);
-    k_seg_fixup<<<blocks, 256, 0, s>>>(w->keys_out, (int)n, t, opt, lr, lr_dev, w->pieces, w->chunk_flags);
-    if (launches) *launches += 2;
+  if (any_sparse) {
+    launch_segment_sums(w, t, n, s, launches);
+    const GSums G = gsums_of(w, t);
+    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    if (maxc_of(t) == 2) k_apply_rows<2><<<blocks, 256, 0, s>>>(w->keys_out, w->seg_start, w->n_uniq, t, G, opt, lr, lr_dev);
+    else k_apply_rows<1><<<blocks, 256, 0, s>>>(w->keys_out, w->seg_start, w->n_uniq, t, G, opt, lr, lr_dev);
+    if (launches) *launches += 1;
   }
   if (any_dense) {
     int ub = (int)((n + 255) / 256); if (ub > 148 * 4) ub = 148 * 4;
