@@ -22,7 +22,10 @@
 #pragma once
 
 constexpr int G0_THREADS = 640;
-constexpr int G0_NE = 4, G0_ND = 3, G0_NW = 2;
+// ring depths: E buffers in tensor memory, Dq buffers, filter-slab stages.  A slab stage is busy for (TMA latency + its
+// MMAs) ~ 1.5 + 0.55 us, so two stages fed the tensor pipe one channel per ~1 us; three stages (and two Dq buffers,
+// which only have to cover the builders' store + fence) fit the same shared memory.
+constexpr int G0_NE = 4, G0_ND = 2, G0_NW = 3;
 constexpr int G0_E = 0, G0_E_STRIDE = 80, G0_D = 320;
 constexpr int G0_DQ_BYTES = 2 * A_STAGE_BYTES;            // 128 rows x 128 columns bf16
 constexpr int G0_WSTAGE = 2 * F0_SLAB_BYTES;
@@ -35,6 +38,7 @@ struct G0Ctl {
 };
 static_assert(sizeof(G0Ctl) <= 256, "control block");
 constexpr int G0_SMEM = 1024 + 2 * A_STAGE_BYTES + G0_ND * G0_DQ_BYTES + G0_NW * G0_WSTAGE + 256;
+static_assert(G0_SMEM <= 227 * 1024, "factorised data gradient exceeds the shared memory of an SM");
 
 struct Dgrad0FactParams {
   CUtensorMap mapW, mapWT;   // Wf0 [q][n][k] and Wf0T [q][k][n], both viewed as [Q16*KA rows][nblk*64 cols], box (64, KA)
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
     uint32_t n = 0;
     for (int t = 0; t < my_tiles; ++t)
       for (int q = 0; q < Q; ++q, ++n) {
-        const int s = n & 1; const uint32_t ph = (n >> 1) & 1;
+        const int s = n % G0_NW; const uint32_t ph = (n / G0_NW) & 1;
         mbar_wait(&ctl->w_empty[s], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&ctl->w_full[s], 2 * slab_bytes);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&ctl->d_empty, (uint32_t)((t & 1) ^ 1));
       for (int q = 0; q < Q; ++q, ++n) {
-        const int s = n & 1; const uint32_t wph = (n >> 1) & 1;
+        const int s = n % G0_NW; const uint32_t wph = (n / G0_NW) & 1;
         const int e1 = (n & 1) * 2; const uint32_t eph = (n >> 1) & 1;
         const uint64_t wT = umma_desc_k_sw128(smem_u32(sW + s * G0_WSTAGE)), wN = umma_desc_k_sw128(smem_u32(sW + s * G0_WSTAGE + F0_SLAB_BYTES));
         mbar_wait(&ctl->w_full[s], wph);

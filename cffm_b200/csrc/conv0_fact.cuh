@@ -25,7 +25,7 @@
 // (included inside namespace cffm::tc of conv_tc.cu, after pack2 / phi_f)
 #pragma once
 
-constexpr int F0_NST = 4;
+constexpr int F0_NST = 6;     // slab ring depth: a stage is busy for (TMA latency + its MMAs), so hiding ~1.8 us of latency behind 0.3 us of MMAs takes 6
 constexpr int F0_KA_MAX = 80;
 constexpr int F0_SLAB_BYTES = 2 * F0_KA_MAX * 128;
 constexpr int F0_THREADS = 480;
@@ -42,13 +42,15 @@ struct F0Ctl {
 constexpr int F0_STAGE_BYTES = 8 * 32 * 32;   // per epilogue warp: [8 w][32 rows][16 channels] bf16
 constexpr int F0_SMEM = 1024 + 2 * A_STAGE_BYTES + F0_NST * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
 static_assert(sizeof(F0Ctl) <= 256, "control block");
+static_assert(F0_SMEM <= 227 * 1024, "factorised forward exceeds the shared memory of an SM");
 // Split mode (CFFM_PREC_BF16X3): the A tile and every weight slab exist as hi and lo halves, Z is split into hi and
 // lo when it is converted (the two bf16 copies fill exactly the columns of the fp32 Z they are made from) and both
-// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of TWO
-// stages of (hi, lo) pairs (a q takes three times as long on the tensor pipe, so two are enough), and the epilogue
-// collects 8 channels instead of 16 (hi and lo tiles share a warp's staging space).
-constexpr int F0S_NST = 2;
-constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
+// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of THREE
+// stages of (hi, lo) pairs (two left the tensor pipe waiting: 2.6 us per channel against 0.85 us of MMAs), and the
+// epilogue collects 8 channels instead of 16; its hi and lo tiles go through ONE 4 KB staging tile per warp, one
+// after the other (that is what makes room for the third stage).
+constexpr int F0S_NST = 3;
+constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * (F0_STAGE_BYTES / 2) + 128;
 static_assert(F0S_SMEM <= 227 * 1024, "split-mode factorised forward exceeds the shared memory of an SM");
 
 struct Fwd0FactParams {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
   constexpr int SLAB_STAGE = (SPLIT ? 2 : 1) * F0_SLAB_BYTES;           // one stage: the slab (hi) [+ its lo half]
   constexpr int AT_BYTES = (SPLIT ? 4 : 2) * A_STAGE_BYTES;             // A tile: [hi: nblk blocks][lo: nblk blocks]
   constexpr int QG = SPLIT ? 8 : 16;                                    // channels an epilogue thread collects per store
+  constexpr int WARP_STAGE = SPLIT ? F0_STAGE_BYTES / 2 : F0_STAGE_BYTES;  // staging tile of an epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B] (split: hi at 0, lo at 2 * A_STAGE_BYTES)
@@ -169,8 +172,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     // Two independent instruction streams coupled by mbarriers only.  All lanes run the loops (uniform control
     // flow); the MMAs and commits of one q sit inside ONE elect.sync region, which ptxas turns into
     // straight-line UTCHMMA issue (a lane == 0 test costs a 16-instruction per-thread loop around every
-    // tcgen05 instruction).  Slab stage = q % NST and D buffer = q & 1 are compile-time (Q % 4 == 0); the Z
-    // buffer index runs modulo 3.
+    // tcgen05 instruction).  The D buffer = q & 1 is compile-time (Q % 4 == 0); the slab ring slot and the Z
+    // buffer index are running counters.
     const uint32_t at_addr = smem_u32(sAt);
     const int ksteps = KA / UMMA_K;
     uint64_t adesc[F0_KA_MAX / UMMA_K];
@@ -181,26 +184,24 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     int zb = 0; uint32_t zph = 0;     // Z buffer of the current q and its phase
     if (warp == 1) {
       const uint32_t idesc1 = umma_idesc_bf16(BM, KA);
-      uint64_t wdesc[NST], wk[F0_KA_MAX / UMMA_K];
-#pragma unroll
-      for (int s = 0; s < NST; ++s) wdesc[s] = umma_desc_k_sw128(smem_u32(sW + s * SLAB_STAGE));
+      uint64_t wk[F0_KA_MAX / UMMA_K];
 #pragma unroll
       for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
       constexpr uint64_t W_LO = (uint64_t)(F0_SLAB_BYTES >> 4);
-      uint32_t it = 0;
+      int ws = 0; uint32_t wph = 0;     // ring slot of the current q and its phase
+      const uint64_t wbase = umma_desc_k_sw128(smem_u32(sW));
       for (int t = 0; t < my_tiles; ++t) {
         mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
         tc_fence_after();
-        for (int q = 0; q < Q; q += 4, ++it) {
+        for (int q = 0; q < Q; q += 4) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            // ring slot of q and its phase: 4 slots -> slot u, phase it & 1;  2 slots -> slot u & 1, phase (u >> 1) & 1
-            mbar_wait(&ctl->full_b[u % NST], NST == 4 ? (it & 1) : (uint32_t)((u >> 1) & 1));
+            mbar_wait(&ctl->full_b[ws], wph);
             mbar_wait(&ctl->z_empty[zb], zph ^ 1);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t d1 = tmem_base + (uint32_t)(F0_Z + zb * F0_Z_STRIDE);
-              const uint64_t wd = wdesc[u % NST];
+              const uint64_t wd = wbase + (uint64_t)(ws * (SLAB_STAGE >> 4));
 #pragma unroll
               for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
                 if (k < ksteps) umma_bf16(d1, adesc[k], wd + wk[k], idesc1, k != 0);
@@ -212,11 +213,12 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
                 for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
                   if (k < ksteps) umma_bf16(d1, adesc[k], wd + W_LO + wk[k], idesc1, true);            // hi * lo
               }
-              umma_commit(&ctl->empty_b[u % NST]);
+              umma_commit(&ctl->empty_b[ws]);
               umma_commit(&ctl->z_full[zb]);
             }
             __syncwarp();
             if (++zb == F0_NZ) { zb = 0; zph ^= 1; }
+            if (++ws == NST) { ws = 0; wph ^= 1; }
           }
         }
       }
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
     const uint32_t d2_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(F0_D2 + qd * 32 + grp * 8);
     float* xch = sbias + F0_BIAS_MAX;             // pooling sums of group 1, [2][128]
     // staging tile of this warp for the TMA store (128-byte aligned, after xch); split: hi tile, then lo tile
-    uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xch + 2 * BM) + 127) & ~(uintptr_t)127) + ew * F0_STAGE_BYTES;
+    uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xch + 2 * BM) + 127) & ~(uintptr_t)127) + ew * WARP_STAGE;
     auto build_a = [&](int tile) {
       const int b = tile * 8 + (r >> 4);
       const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
@@ -361,11 +363,20 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
           __syncwarp();
           if constexpr (SPLIT) {
+            // hi tile, its store, then the lo tile through the same 4 KB
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < 8; ++w)
               *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
-              *reinterpret_cast<uint4*>(stage + F0_STAGE_BYTES / 2 + (w * 32 + lane) * 16) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
-            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8); tma_store_wait_read(); }
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_3d(&prm.mapX2, stage, q0, tile * BM + qd * 32, grp * 8);
           } else {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -373,12 +384,9 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
               d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
               d[1] = make_uint4(acc[w][QG / 2 - 4], acc[w][QG / 2 - 3], acc[w][QG / 2 - 2], acc[w][QG / 2 - 1]);
             }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
-            if (SPLIT) tma_store_3d(&prm.mapX2, stage + F0_STAGE_BYTES / 2, q0, tile * BM + qd * 32, grp * 8);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8);
           }
         } else if (b < prm.B) {
           const int64_t off = (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
