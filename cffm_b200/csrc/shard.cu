@@ -9,8 +9,8 @@
 //             The step then computes on the received rows ("mini tables", one row per unique id of the local
 //             batch) with the ids renumbered to positions in that list: every kernel of forward.cu / backward.cu
 //             runs unchanged.
-//   backward  per-sample gradient rows -> summed per unique id on the requesting rank FIRST (order of appearance)
-//             -> all-to-all of the sums to the owners -> owner: sort by local row + segmented sum over the
+//   backward  per-sample gradient rows -> summed per unique id on the requesting rank FIRST (phase 1 of update.cu:
+//             the summation order of a single device) -> all-to-all of the sums to the owners -> owner: sort by local row + segmented sum over the
 //             requesting ranks in rank order + sparse optimizer update of its shard (update.cu, unchanged).
 //
 // Traffic per rank and step: U * (4 + 4*(Ki+Ko+1)) bytes each way for U unique ids (vs. world * B * F rows for the
