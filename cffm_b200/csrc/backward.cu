@@ -383,31 +383,29 @@ struct InnerDenseGradArgs {
 };
 template <int ACT>
 __global__ void k_inner_dense_grad(const InnerDenseGradArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // a thread takes two neighbouring flattened elements (p, w, o = 0 / 1) = the two taps of one conv position
+  const int idx = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int PK = a.P * a.K, K = a.K, F = a.F;
-  const bool ok = idx < PK;
-  const int p = ok ? idx >> a.lgK : 0, k = idx & (K - 1);
+  if (idx >= PK) return;
+  const int p = idx >> a.lgK, k = idx & (K - 1);
   const int fi = a.pair_i[p], fj = a.pair_j[p];
-  const int o = idx & 1;
-  const float wt0 = __ldg(a.cw + o), wt1 = __ldg(a.cw + 2 + o), cbo = __ldg(a.cb + o);
+  const float w00 = __ldg(a.cw + 0), w01 = __ldg(a.cw + 1), w10 = __ldg(a.cw + 2), w11 = __ldg(a.cw + 3);
+  const float c0 = __ldg(a.cb + 0), c1 = __ldg(a.cb + 1);
   const int c = blockIdx.y;
   const int rpc = (a.B + a.C - 1) / a.C;
   const int b0 = c * rpc, b1 = min(a.B, b0 + rpc);
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
   for (int b = b0; b < b1; ++b) {   // two dependent loads per sample (id, then row): keep four samples in flight
-    float A = 0.f;
-    if (ok) {
-      const float ei = __ldg(a.tab + (int64_t)__ldg(a.ids + (int64_t)b * F + fi) * K + k);
-      const float ej = __ldg(a.tab + (int64_t)__ldg(a.ids + (int64_t)b * F + fj) * K + k);
-      A = act_f<ACT>(ei * ej);
-    }
-    const float Ao = __shfl_xor_sync(0xffffffffu, A, 1);
-    const float a0 = o ? Ao : A, a1 = o ? A : Ao;
-    const float y = fmaf(a1, wt1, a0 * wt0) + cbo;
-    s = fmaf(__ldg(a.gout + b), phi_f<ACT>(y) + fmaxf(a0, a1), s);
+    const float2 ei = __ldg(reinterpret_cast<const float2*>(a.tab + (int64_t)__ldg(a.ids + (int64_t)b * F + fi) * K + k));
+    const float2 ej = __ldg(reinterpret_cast<const float2*>(a.tab + (int64_t)__ldg(a.ids + (int64_t)b * F + fj) * K + k));
+    const float a0 = act_f<ACT>(ei.x * ej.x), a1 = act_f<ACT>(ei.y * ej.y);
+    const float y0 = fmaf(a1, w10, a0 * w00) + c0, y1 = fmaf(a1, w11, a0 * w01) + c1;
+    const float mx = fmaxf(a0, a1), g = __ldg(a.gout + b);
+    s0 = fmaf(g, phi_f<ACT>(y0) + mx, s0);
+    s1 = fmaf(g, phi_f<ACT>(y1) + mx, s1);
   }
-  if (ok) a.partial[(int64_t)c * PK + idx] = s;
+  *reinterpret_cast<float2*>(a.partial + (int64_t)c * PK + idx) = make_float2(s0, s1);
 }
 
 // d bias_W[f,q] = sum_b fb[b,f] * dz[b,q]/tau
@@ -656,7 +654,7 @@ int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, in
       d.ids = ids; d.B = B; d.F = F; d.P = P; d.K = m->Ki; d.lgK = ilog2(m->Ki);
       d.tab = tv.inner; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
       d.pair_i = m->pair_i; d.pair_j = m->pair_j; d.partial = part + pl.off_Wd; d.C = pl.Cb;
-      dim3 grid(ceil_div((int64_t)P * m->Ki, 256), pl.Cb);
+      dim3 grid(ceil_div((int64_t)P * m->Ki / 2, 256), pl.Cb);
       CFFM_PROF(m, "inner_dense_grad", s);
       CFFM_DISPATCH_ACT(act, k_inner_dense_grad<ACT><<<grid, 256, 0, s>>>(d));
       m->launches++;

@@ -1290,7 +1290,9 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       const int chunks_total = (int)((rows + BK - 1) / BK);
       // split factor: fill whole waves of 148 persistent CTAs (units = tiles * split)
       int want = 1; double best = 0.0;
-      const int max_split = (int)std::min<int64_t>(st->wg_partial_floats / (4ll * Pp * Pp), chunks_total);
+      // (a split needs work to amortise: at least 32 reduction chunks each -- at the reference's dataset sizes a 74-way
+      // split left 14 chunks per CTA and a partial-sum reduction that took twice as long as the GEMM)
+      const int max_split = (int)std::min<int64_t>(st->wg_partial_floats / (4ll * Pp * Pp), std::max(1, chunks_total / 32));
       for (int sfac = 1; sfac <= max_split && sfac * tiles <= 4 * 148; ++sfac) {
         const int units = sfac * tiles;
         const double eff = (double)units / (148.0 * ((units + 147) / 148));
@@ -1395,7 +1397,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       if (l == 0 && st->Wf0T && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
       const int64_t rows = (int64_t)B * (K >> (l + 1)) * (K >> (l + 1));
       a.X[nl] = st->dY[l]; a.Xlo[nl] = st->dYlo[l]; a.rows[nl] = rows;
-      a.C[nl] = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
+      a.C[nl] = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));   // few chunks: the second stage walks them one by one
       a.out_off[nl] = m->lay.conv_b[l];
       maxC = std::max(maxC, a.C[nl]);
       ++nl;

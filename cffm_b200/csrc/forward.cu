@@ -72,23 +72,26 @@ __global__ void k_inner_linear_fwd(const InnerLinArgs a) {
       *reinterpret_cast<float4*>(e + f * K + 4 * c) = v;
     }
     __syncwarp();
-    const int o = lane & 1;
-    const float wt0 = __ldg(a.cw + o), wt1 = __ldg(a.cw + 2 + o), cbo = __ldg(a.cb + o);  // W[0,t,0,o] -> t*2+o
+    // a lane takes two neighbouring k (the two taps of one conv position, K is even): both output channels of the
+    // position come out of one lane, no exchange between lanes, 64 elements per pass
+    const float w00 = __ldg(a.cw + 0), w01 = __ldg(a.cw + 1), w10 = __ldg(a.cw + 2), w11 = __ldg(a.cw + 3);  // W[0,t,0,o] -> t*2+o
+    const float c0 = __ldg(a.cb + 0), c1 = __ldg(a.cb + 1);
     const int PK = P * K;
     float acc = 0.f;
-    for (int base = 0; base < PK; base += 32) {
-      const int idx = base + lane;
-      const bool ok = idx < PK;
-      float A = 0.f;
-      if (ok) {
+    for (int base = 0; base < PK; base += 64) {
+      const int idx = base + 2 * lane;
+      if (idx < PK) {
         const int p = idx >> a.lgK, k = idx & (K - 1);
-        A = act_f<ACT>(e[s_pi[p] * K + k] * e[s_pj[p] * K + k]);  // :310, :319
+        const float2 ei = *reinterpret_cast<const float2*>(e + s_pi[p] * K + k);
+        const float2 ej = *reinterpret_cast<const float2*>(e + s_pj[p] * K + k);
+        const float a0 = act_f<ACT>(ei.x * ej.x), a1 = act_f<ACT>(ei.y * ej.y);   // :310, :319  taps 2w, 2w+1
+        const float y0 = fmaf(a1, w10, a0 * w00) + c0;                            // :327 conv + bias, o = 0
+        const float y1 = fmaf(a1, w11, a0 * w01) + c1;                            //                   o = 1
+        const float mx = fmaxf(a0, a1);                                           // :331-332
+        const float2 wd = __ldg(reinterpret_cast<const float2*>(a.Wd + idx));     // :333 flatten (p,w,o), :339
+        acc = fmaf(phi_f<ACT>(y0) + mx, wd.x, acc);                               // :478, :330
+        acc = fmaf(phi_f<ACT>(y1) + mx, wd.y, acc);
       }
-      const float Ao = __shfl_xor_sync(0xffffffffu, A, 1);
-      const float a0 = o ? Ao : A, a1 = o ? A : Ao;       // taps 2w, 2w+1
-      const float y = fmaf(a1, wt1, a0 * wt0) + cbo;       // :327 conv + bias
-      const float r = phi_f<ACT>(y) + fmaxf(a0, a1);       // :478, :330, :331-332
-      if (ok) acc = fmaf(r, __ldg(a.Wd + idx), acc);       // :333 flatten (p,w,o), :339
     }
     acc = warp_sum(acc);
     if (lane == 0) a.comp_inner[b] = acc + __ldg(a.bd);
