@@ -78,6 +78,7 @@ __global__ void k_inner_linear_fwd(const InnerLinArgs a) {
     const float c0 = __ldg(a.cb + 0), c1 = __ldg(a.cb + 1);
     const int PK = P * K;
     float acc = 0.f;
+#pragma unroll 4   // the dense-weight loads of four passes go out together: a pass no longer waits for its own
     for (int base = 0; base < PK; base += 64) {
       const int idx = base + 2 * lane;
       if (idx < PK) {
