@@ -133,6 +133,8 @@ def _declare(lib):
         "cffm_get_opt_step": (C.c_int, [vp, P(i64)]),
         "cffm_set_opt_step": (C.c_int, [vp, i64]),
         "cffm_uses_graph": (C.c_int, [vp]),
+        "cffm_debug_check_guards": (C.c_int, [C.c_char_p, i32]),
+        "cffm_debug_guard_selftest": (C.c_int, []),
         "cffm_forward_dev": (C.c_int, [vp, vp, i64, vp, vp]),
         "cffm_forward_host": (C.c_int, [vp, vp, i64, vp]),
         "cffm_train_step_dev": (C.c_int, [vp, vp, vp, i64, vp, vp]),

@@ -85,6 +85,9 @@ extern "C" int cffm_synchronize(cffm_handle* h) {
   return CFFM_OK;
 }
 
+extern "C" int cffm_debug_check_guards(char* msg, int32_t cap) { return dev_check_guards(msg, cap); }
+extern "C" int cffm_debug_guard_selftest(void) { return dev_guard_selftest(); }
+
 extern "C" int cffm_uses_graph(const cffm_handle* h) { return h && h->m.use_graph ? 1 : 0; }
 
 extern "C" int64_t cffm_launch_count(const cffm_handle* h) { return h ? h->m.launches : 0; }
@@ -462,9 +465,9 @@ extern "C" int cffm_evaluate_host(cffm_handle* h, const int32_t* ids_host, const
   if (m->pending) { m->err = "cffm_train_flush the pipelined steps first"; return CFFM_ERR_INVALID; }
   const int F = m->F;
   float* y_dev = nullptr;
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&y_dev, sizeof(float) * N));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&y_dev, sizeof(float) * N));
   cudaError_t e = cudaMemcpyAsync(y_dev, labels_host, sizeof(float) * N, cudaMemcpyHostToDevice, m->stream);
-  if (e != cudaSuccess) { cudaFree(y_dev); m->err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
+  if (e != cudaSuccess) { dev_free(y_dev); m->err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
   k_label_stats<<<1, 1024, 0, m->stream>>>(y_dev, N, m->eval_acc);
   m->launches++;
   int rc = CFFM_OK;
@@ -484,7 +487,7 @@ extern "C" int cffm_evaluate_host(cffm_handle* h, const int32_t* ids_host, const
   double acc[5] = {0, 0, 0, 0, 0};
   e = cudaMemcpyAsync(acc, m->eval_acc, sizeof(acc), cudaMemcpyDeviceToHost, m->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
-  cudaFree(y_dev);
+  dev_free(y_dev);
   if (rc != CFFM_OK) return rc;
   if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
   const double sse = acc[4], n = (double)N;
@@ -515,14 +518,14 @@ extern "C" int cffm_dataset_upload(cffm_handle* h, const int32_t* ids_host, cons
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   CFFM_CUDA_OK(m, cudaStreamSynchronize(m->stream));
   void* old[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
-  for (void* p : old) if (p) cudaFree(p);
+  for (void* p : old) if (p) dev_free(p);
   m->ds_ids = m->ds_ids_tmp = nullptr; m->ds_labels = m->ds_labels_tmp = nullptr; m->ds_perm = nullptr; m->ds_N = 0;
   const int F = m->F;
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_ids, sizeof(int32_t) * N * F));
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_ids_tmp, sizeof(int32_t) * N * F));
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_labels, sizeof(float) * N));
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_labels_tmp, sizeof(float) * N));
-  CFFM_CUDA_OK(m, cudaMalloc((void**)&m->ds_perm, sizeof(int64_t) * N));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&m->ds_ids, sizeof(int32_t) * N * F));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&m->ds_ids_tmp, sizeof(int32_t) * N * F));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&m->ds_labels, sizeof(float) * N));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&m->ds_labels_tmp, sizeof(float) * N));
+  CFFM_CUDA_OK(m, dev_malloc((void**)&m->ds_perm, sizeof(int64_t) * N));
   CFFM_CUDA_OK(m, cudaMemcpy(m->ds_ids, ids_host, sizeof(int32_t) * N * F, cudaMemcpyHostToDevice));
   CFFM_CUDA_OK(m, cudaMemcpy(m->ds_labels, labels_host, sizeof(float) * N, cudaMemcpyHostToDevice));
   m->ds_N = N;
@@ -690,10 +693,10 @@ extern "C" int cffm_debug_fetch(cffm_handle* h, const char* what, float* host_ds
       if (n_out) *n_out = n;
       if (!host_dst || cap <= 0) return CFFM_OK;
       float* tmp = nullptr;
-      CFFM_CUDA_OK(m, cudaMalloc((void**)&tmp, sizeof(float) * n));
+      CFFM_CUDA_OK(m, dev_malloc((void**)&tmp, sizeof(float) * n));
       int r = tc_debug_fetch(m, grad, l, tmp, B * H * H);
       if (r == CFFM_OK) cudaMemcpy(host_dst, tmp, sizeof(float) * std::min(cap, n), cudaMemcpyDeviceToHost);
-      cudaFree(tmp);
+      dev_free(tmp);
       return r;
     }
     src = grad ? m->dY[l] : m->Y[l];
@@ -705,10 +708,10 @@ extern "C" int cffm_debug_fetch(cffm_handle* h, const char* what, float* host_ds
     if (src) CFFM_CUDA_OK(m, cudaMemcpy(host_dst, src, sizeof(float) * k, cudaMemcpyDeviceToHost));
     else {
       float* tmp = nullptr;
-      CFFM_CUDA_OK(m, cudaMalloc((void**)&tmp, sizeof(float) * k));
+      CFFM_CUDA_OK(m, dev_malloc((void**)&tmp, sizeof(float) * k));
       k_i32_to_f32<<<ceil_div(k, 256), 256>>>(isrc, tmp, k);
       cudaError_t e = cudaMemcpy(host_dst, tmp, sizeof(float) * k, cudaMemcpyDeviceToHost);
-      cudaFree(tmp);
+      dev_free(tmp);
       if (e != cudaSuccess) { m->err = cudaGetErrorString(e); return CFFM_ERR_CUDA; }
     }
   }

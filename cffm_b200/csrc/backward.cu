@@ -426,7 +426,7 @@ __global__ void k_att_outer(const float* __restrict__ fb, const float* __restric
 template <class T>
 static int dmalloc(Model* m, T** p, int64_t n) {
   if (n <= 0) n = 1;
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (size_t)n);
+  cudaError_t e = dev_malloc((void**)p, sizeof(T) * (size_t)n);
   if (e != cudaSuccess) {
     m->err = std::string("cudaMalloc(") + std::to_string(sizeof(T) * (size_t)n) + " B): " + cudaGetErrorString(e);
     *p = nullptr;

@@ -84,6 +84,15 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Device allocations of the library go through these two.  With CFFM_GUARD=1 in the environment (read once) every
+// allocation gets a 4 KB band on either side filled with a pattern; cffm_debug_check_guards() verifies the bands, i.e.
+// that no kernel wrote just outside one of its buffers (compute-sanitizer is closed on this GPU pool).
+cudaError_t dev_malloc(void** p, size_t bytes);
+cudaError_t dev_free(void* p);
+// number of allocations whose bands are damaged (and a description of the first) -- synchronises the device
+int dev_check_guards(char* msg, int cap);
+int dev_guard_selftest();   // 0: an overrun by one element on either side is detected; -1: guard off
+
 // cudaFuncSetAttribute is per device (context): a "done" flag has to be kept per device ordinal, or a second
 // handle on another GPU of the same process launches without its shared-memory opt-in.
 struct PerDeviceOnce {

@@ -947,7 +947,7 @@ static int pick_bn(int Pp) {  // largest multiple of 64 (<= 256) dividing Pp
 
 template <class T>
 static int tcmalloc(Model* m, T** p, int64_t n) {
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (size_t)(n > 0 ? n : 1));
+  cudaError_t e = dev_malloc((void**)p, sizeof(T) * (size_t)(n > 0 ? n : 1));
   if (e != cudaSuccess) { m->err = std::string("cudaMalloc (bf16 path): ") + cudaGetErrorString(e); *p = nullptr; return CFFM_ERR_NOMEM; }
   return CFFM_OK;
 }
@@ -1044,21 +1044,21 @@ int tc_alloc(Model* m, bool train) {
 void tc_free(Model* m) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   if (!st) return;
-  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) cudaFree(st->X[l]); if (st->Xlo[l]) cudaFree(st->Xlo[l]); }
+  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) dev_free(st->X[l]); if (st->Xlo[l]) dev_free(st->Xlo[l]); }
   for (int l = 0; l < kMaxConv; ++l) {
-    if (st->dY[l]) cudaFree(st->dY[l]); if (st->Wt[l]) cudaFree(st->Wt[l]); if (st->Wd[l]) cudaFree(st->Wd[l]);
-    if (st->dYlo[l]) cudaFree(st->dYlo[l]); if (st->Wtlo[l]) cudaFree(st->Wtlo[l]); if (st->Wdlo[l]) cudaFree(st->Wdlo[l]);
+    if (st->dY[l]) dev_free(st->dY[l]); if (st->Wt[l]) dev_free(st->Wt[l]); if (st->Wd[l]) dev_free(st->Wd[l]);
+    if (st->dYlo[l]) dev_free(st->dYlo[l]); if (st->Wtlo[l]) dev_free(st->Wtlo[l]); if (st->Wdlo[l]) dev_free(st->Wdlo[l]);
   }
-  if (st->wg_partial) cudaFree(st->wg_partial);
-  if (st->bg_partial) cudaFree(st->bg_partial);
-  if (st->pool_part) cudaFree(st->pool_part);
-  if (st->Wf0) cudaFree(st->Wf0);
-  if (st->Wf0lo) cudaFree(st->Wf0lo);
-  if (st->Wf0T) cudaFree(st->Wf0T);
-  if (st->pterm0) cudaFree(st->pterm0);
-  if (st->df_bpart) cudaFree(st->df_bpart);
-  if (st->wf_part) cudaFree(st->wf_part);
-  if (st->A8) cudaFree(st->A8);
+  if (st->wg_partial) dev_free(st->wg_partial);
+  if (st->bg_partial) dev_free(st->bg_partial);
+  if (st->pool_part) dev_free(st->pool_part);
+  if (st->Wf0) dev_free(st->Wf0);
+  if (st->Wf0lo) dev_free(st->Wf0lo);
+  if (st->Wf0T) dev_free(st->Wf0T);
+  if (st->pterm0) dev_free(st->pterm0);
+  if (st->df_bpart) dev_free(st->df_bpart);
+  if (st->wf_part) dev_free(st->wf_part);
+  if (st->A8) dev_free(st->A8);
   delete st;
   m->tcs = nullptr;
 }

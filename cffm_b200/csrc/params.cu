@@ -8,7 +8,104 @@
 #include "common.cuh"
 #include "model.h"
 
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
 namespace cffm {
+
+// ---- guarded device allocations (common.cuh) -------------------------------------------------
+namespace {
+constexpr size_t kGuard = 4096;
+constexpr uint32_t kPattern = 0xA5C3F00Du;
+struct GuardRec { void* base; size_t bytes; };
+std::mutex g_guard_mu;
+std::unordered_map<void*, GuardRec> g_guard;   // user pointer -> allocation
+bool guard_on() { static const bool on = [] { const char* e = getenv("CFFM_GUARD"); return e && e[0] == '1'; }(); return on; }
+__global__ void k_guard_fill(uint32_t* p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = kPattern;
+}
+__global__ void k_guard_check(const uint32_t* p, size_t n, int* bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && p[i] != kPattern) atomicAdd(bad, 1);
+}
+}  // namespace
+
+cudaError_t dev_malloc(void** p, size_t bytes) {
+  if (!guard_on()) return cudaMalloc(p, bytes);
+  const size_t body = (bytes + 255) & ~size_t(255);
+  void* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, body + 2 * kGuard);
+  if (e != cudaSuccess) { *p = nullptr; return e; }
+  const size_t nw = kGuard / 4;
+  k_guard_fill<<<(unsigned)((nw + 255) / 256), 256>>>(reinterpret_cast<uint32_t*>(base), nw);
+  // the tail band starts right after the requested bytes (rounded up to 4): an overrun by one element is seen
+  const size_t tail_off = kGuard + ((bytes + 3) & ~size_t(3));
+  k_guard_fill<<<(unsigned)((nw + 255) / 256), 256>>>(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(base) + tail_off), nw);
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(base); *p = nullptr; return e; }
+  *p = reinterpret_cast<char*>(base) + kGuard;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guard[*p] = GuardRec{base, bytes};
+  return cudaSuccess;
+}
+
+cudaError_t dev_free(void* p) {
+  if (!p) return cudaSuccess;
+  if (guard_on()) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    auto it = g_guard.find(p);
+    if (it != g_guard.end()) { void* base = it->second.base; g_guard.erase(it); return cudaFree(base); }
+  }
+  return cudaFree(p);
+}
+
+int dev_check_guards(char* msg, int cap) {
+  if (msg && cap > 0) msg[0] = 0;
+  if (!guard_on()) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) { if (msg) snprintf(msg, cap, "device error before the guard check"); return -1; }
+  int* bad_d = nullptr;
+  if (cudaMalloc((void**)&bad_d, sizeof(int)) != cudaSuccess) return -1;
+  int damaged = 0;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  for (auto& kv : g_guard) {
+    const GuardRec& r = kv.second;
+    const size_t nw = kGuard / 4;
+    const size_t tail_off = kGuard + ((r.bytes + 3) & ~size_t(3));
+    int bad[2] = {0, 0};
+    for (int side = 0; side < 2; ++side) {
+      cudaMemset(bad_d, 0, sizeof(int));
+      const char* at = reinterpret_cast<const char*>(r.base) + (side ? tail_off : 0);
+      k_guard_check<<<(unsigned)((nw + 255) / 256), 256>>>(reinterpret_cast<const uint32_t*>(at), nw, bad_d);
+      cudaMemcpy(&bad[side], bad_d, sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    if (bad[0] || bad[1]) {
+      if (!damaged && msg) snprintf(msg, cap, "allocation of %zu bytes: %d words damaged below, %d above", r.bytes, bad[0], bad[1]);
+      ++damaged;
+    }
+  }
+  cudaFree(bad_d);
+  return damaged;
+}
+
+// self-test of the checker: a guarded buffer of 100 floats, element 100 (one past the end) and element -1 written
+__global__ void k_guard_poke(float* p, int i) { p[i] = 1.f; }
+int dev_guard_selftest() {
+  if (!guard_on()) return -1;
+  float* p = nullptr;
+  if (dev_malloc((void**)&p, 100 * sizeof(float)) != cudaSuccess) return -2;
+  char msg[128];
+  const int before = dev_check_guards(msg, sizeof(msg));
+  k_guard_poke<<<1, 1>>>(p, 100);
+  const int after_hi = dev_check_guards(msg, sizeof(msg));
+  k_guard_poke<<<1, 1>>>(p, -1);
+  const int after_lo = dev_check_guards(msg, sizeof(msg));
+  dev_free(p);
+  const int end = dev_check_guards(msg, sizeof(msg));
+  return (after_hi == before + 1 && after_lo == before + 1 && end == before) ? 0 : 1;
+}
 
 static int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
 
@@ -222,7 +319,7 @@ int model_init_params(Model* m, uint64_t seed) {
 template <class T>
 static int dmalloc(Model* m, T** p, int64_t n) {
   if (n <= 0) n = 1;
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (size_t)n);
+  cudaError_t e = dev_malloc((void**)p, sizeof(T) * (size_t)n);
   if (e != cudaSuccess) {
     m->err = std::string("cudaMalloc(") + std::to_string(sizeof(T) * (size_t)n) + " B): " + cudaGetErrorString(e);
     *p = nullptr;
@@ -309,9 +406,9 @@ void model_free(Model* m) {
   shard_free(m);
   tc_free(m);
   void* ds[] = {m->ds_ids, m->ds_ids_tmp, m->ds_labels, m->ds_labels_tmp, m->ds_perm};
-  for (void* p : ds) if (p) cudaFree(p);
-  for (void* p : dev) if (p) cudaFree(p);
-  for (int l = 0; l < kMaxConv; ++l) { if (m->Y[l]) cudaFree(m->Y[l]); if (m->dY[l]) cudaFree(m->dY[l]); }
+  for (void* p : ds) if (p) dev_free(p);
+  for (void* p : dev) if (p) dev_free(p);
+  for (int l = 0; l < kMaxConv; ++l) { if (m->Y[l]) dev_free(m->Y[l]); if (m->dY[l]) dev_free(m->dY[l]); }
   for (int s = 0; s < 2; ++s) {
     if (m->h_ids[s]) cudaFreeHost(m->h_ids[s]);
     if (m->h_labels[s]) cudaFreeHost(m->h_labels[s]);

@@ -102,7 +102,7 @@ __global__ void k_gather_scalar(const float* __restrict__ tab, const int32_t* __
 // ---------------------------------------------------------------------------------------------
 template <class T>
 static int smalloc(Model* m, T** p, int64_t n) {
-  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (size_t)(n > 0 ? n : 1));
+  cudaError_t e = dev_malloc((void**)p, sizeof(T) * (size_t)(n > 0 ? n : 1));
   if (e != cudaSuccess) { m->err = std::string("cudaMalloc (sharded tables): ") + cudaGetErrorString(e); *p = nullptr; return CFFM_ERR_NOMEM; }
   return CFFM_OK;
 }
@@ -141,7 +141,7 @@ void shard_free(Model* m) {
   if (!ss) return;
   void* p[] = {ss->keys, ss->uniq_rows, ss->counts, ss->all_counts, ss->ids_remap, ss->mini_inner, ss->mini_outer, ss->mini_bias,
                ss->req_rows, ss->x_inner, ss->x_outer, ss->x_bias};
-  for (void* q : p) if (q) cudaFree(q);
+  for (void* q : p) if (q) dev_free(q);
   if (ss->h_counts) cudaFreeHost(ss->h_counts);
   sparse_work_free(&ss->sw_req);
   delete ss;

@@ -228,7 +228,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, int gcols, std::string* err) {
   w->cub_tmp_bytes = sizeof(int32_t) * (size_t)(ntiles * 256 + ntiles + 16);   // digit offsets + per-tile head counts
   cudaError_t e;
 #define SW_ALLOC(ptr, bytes)                                                        \
-  e = cudaMalloc((void**)&(ptr), (bytes));                                           \
+  e = dev_malloc((void**)&(ptr), (bytes));                                           \
   if (e != cudaSuccess) { if (err) *err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CFFM_ERR_NOMEM; }
   SW_ALLOC(w->keys_out, sizeof(int32_t) * cap);
   SW_ALLOC(w->vals, sizeof(int32_t) * cap);
@@ -253,7 +253,7 @@ int sparse_work_alloc(SparseWork* w, int64_t cap, int gcols, std::string* err) {
 
 void sparse_work_free(SparseWork* w) {
   void* p[] = {w->keys_out, w->vals, w->vals_out, w->seg_start, w->n_uniq, w->flags, w->cub_tmp, w->pieces, w->chunk_flags, w->gsum};
-  for (void* q : p) if (q) cudaFree(q);
+  for (void* q : p) if (q) dev_free(q);
   *w = SparseWork();
 }
 

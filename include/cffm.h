@@ -203,6 +203,14 @@ int cffm_op_gemm_bf16_tn_dev(const void* a_dev, const void* b_dev, float* c_dev,
 /* message of the last failed tensor-core launch on this thread */
 const char* cffm_tc_last_error(void);
 
+/* ---- own bounds check (compute-sanitizer is not available on the GPU pool this was built on): with CFFM_GUARD=1 in
+ *      the environment every device allocation of the library carries a 4 KB pattern band on either side; this call
+ *      synchronises and returns the number of allocations whose bands were written to (0 = clean, also when the
+ *      guard is off; negative: error).  msg (may be NULL) receives a description of the first damaged one. */
+int cffm_debug_check_guards(char* msg, int32_t cap);
+/* checks the checker: 0 = a write one element before / after a guarded buffer is reported; -1 = CFFM_GUARD is off */
+int cffm_debug_guard_selftest(void);
+
 /* ---- intermediate tensors of the last forward / train step, for parity tests ---------------
  * what: "out", "final2", "final", "linear", "t1", "outer_rows", "conv_<l>" (pre-activation Y_l),
  *       "grad_out", "grad_inner_rows", "grad_outer_rows", "grad_bias_rows", "dense_grads",
