@@ -42,6 +42,21 @@ def main():
     sid, sy = shard_batch(ids[2], y[2], rank, world)
     pred = eng.forward(sid)
     res["losses"] = losses
+    # checkpoint of a sharded run: every rank saves / restores its own shard (+ replicated dense variables, slots, step)
+    state = eng.state_dict()
+    eng2 = Engine(M, F, 32, 32, activation="selu", max_batch=B // world, precision=precision, device=local, seed=99,
+                  optimizer=optimizer, lr=lr, shard=(rank, world))
+    bind_engine(eng2, dist)
+    eng2.load_state_dict(state)
+    sid0, sy0 = shard_batch(ids[0], y[0], rank, world)
+    la, lb = eng.train_step(sid0, sy0), eng2.train_step(sid0, sy0)
+    sa, sb = eng.state_dict(), eng2.state_dict()
+    res["resume_identical"] = bool(la == lb and all(np.array_equal(np.asarray(sa[k]), np.asarray(sb[k])) for k in sa))
+    res["shard_rows_in_state"] = int(state["w:inner_embeddings"].shape[0])
+    eng2.close()
+    ok = torch.tensor([1.0 if res["resume_identical"] else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    res["resume_identical"] = bool(ok.item() == 1.0)
     w = {k: gather_table(eng, k, dist) for k in eng.param_infos()}
     preds = [None] * world
     dist.all_gather_object(preds, pred)
@@ -51,6 +66,7 @@ def main():
         # identical initial weights: the sharded initialiser draws the values of the replicated layout
         ref.set_param("feature_bias", fb)
         ref_losses = [ref.train_step(ids[s], y[s]) for s in range(3)]
+        ref.train_step(ids[0], y[0])                       # the extra step of the resume check above
         rw = ref.get_weights()
         ref_pred = ref.forward(ids[2])
         res["ref_losses"] = ref_losses

@@ -48,6 +48,7 @@ def test_row_sharded_tables_equal_single_gpu(tmp_path, precision, optimizer):
     res = json.load(open(out))
     assert res["local_rows"] == 351                     # 701 rows over two ranks: 351 + 350
     assert res["untouched_rows_bit_identical"] and res["init_identical"]
+    assert res["resume_identical"] and res["shard_rows_in_state"] == 351      # per-rank checkpoint: save -> new handle -> same next step
     tol = 1e-4 if precision == "fp32" else 2e-2
     for a, b in zip(res["losses"], res["ref_losses"]):
         assert abs(a - b) <= tol * max(1.0, abs(b)), (res["losses"], res["ref_losses"])
