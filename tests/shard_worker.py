@@ -66,9 +66,9 @@ def main():
         # identical initial weights: the sharded initialiser draws the values of the replicated layout
         ref.set_param("feature_bias", fb)
         ref_losses = [ref.train_step(ids[s], y[s]) for s in range(3)]
+        ref_pred = ref.forward(ids[2])
         ref.train_step(ids[0], y[0])                       # the extra step of the resume check above
         rw = ref.get_weights()
-        ref_pred = ref.forward(ids[2])
         res["ref_losses"] = ref_losses
         res["pred_max_abs_diff"] = float(np.max(np.abs(np.concatenate(preds) - ref_pred)))
         res["pred_scale"] = float(np.max(np.abs(ref_pred)))
