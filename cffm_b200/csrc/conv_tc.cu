@@ -86,6 +86,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
   CUtensorMap mapA, mapB, mapA2, mapB2;   // *2: the lo halves (split mode)
   Geom g;
   SplitK sk; bf16* Xout_lo;
+  bf16* Dphi;               // gelu, training: phi'(Y) next to X = phi(Y) (its derivative does not follow from X's sign)
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
   float* pool_part;         // l >= 1, tiles_n > 1: pooled sums per N tile [tiles_n][B*Ho], added up by k_pool_parts
   const float* rows; const int* pair_i; const int* pair_j;
@@ -212,6 +213,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
       if (L0 && n0 >= p.g.Pp) return;     // N tiles may overhang the padded channel count (zero weights)
       uint32_t pk[16];
       uint32_t pl[SPLIT ? 16 : 1];
+      uint32_t pd[ACT == CFFM_ACT_GELU ? 16 : 1];
       float bv[32];
       if (L0) {
 #pragma unroll
@@ -231,6 +233,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
         rowsum += x0 + x1;
         pk[j >> 1] = pack2(x0, x1);
         if constexpr (SPLIT) pl[j >> 1] = pack2_lo(x0, x1);
+        if constexpr (ACT == CFFM_ACT_GELU) pd[j >> 1] = pack2(phi_df<ACT>(y0), phi_df<ACT>(y1));
       }
       if (m < p.g.M) {
         uint4* dst = reinterpret_cast<uint4*>(p.Xout + (int64_t)m * p.g.Pp + n0);
@@ -240,6 +243,13 @@ struct ConvFwdTC : KMajorA, KMajorB {
           uint4* dl = reinterpret_cast<uint4*>(p.Xout_lo + (int64_t)m * p.g.Pp + n0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) dl[q4] = make_uint4(pl[4 * q4], pl[4 * q4 + 1], pl[4 * q4 + 2], pl[4 * q4 + 3]);
+        }
+        if constexpr (ACT == CFFM_ACT_GELU) {
+          if (p.Dphi) {
+            uint4* dd = reinterpret_cast<uint4*>(p.Dphi + (int64_t)m * p.g.Pp + n0);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) dd[q4] = make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
+          }
         }
       }
     }
@@ -354,6 +364,10 @@ struct ConvDgradTC : KMajorA, KMajorB {
         }
       }
     }
+    static __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+      const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    }
     static __device__ __forceinline__ uint32_t keep_bits(uint32_t x) {   // X > 0  <=>  Y > 0, per bf16 half
       return ((x & 0x7FFFu) ? 0xFFFFu : 0u) | ((x & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
     }
@@ -383,7 +397,11 @@ struct ConvDgradTC : KMajorA, KMajorB {
       for (int i = 0; i < 4; ++i) {
         uint4 d = *reinterpret_cast<const uint4*>(stg + ((lane >> 2) + 8 * i) * STG + (lane & 3) * 16);
         const uint4 x = mk[SPLIT ? 0 : ci][i];
-        d.x &= keep_bits(x.x); d.y &= keep_bits(x.y); d.z &= keep_bits(x.z); d.w &= keep_bits(x.w);
+        if constexpr (ACT == CFFM_ACT_GELU) {   // p.X points at phi'(Y): multiply (bf16 x bf16 -> bf16)
+          d.x = mul_bf16x2(d.x, x.x); d.y = mul_bf16x2(d.y, x.y); d.z = mul_bf16x2(d.z, x.z); d.w = mul_bf16x2(d.w, x.w);
+        } else {
+          d.x &= keep_bits(x.x); d.y &= keep_bits(x.y); d.z &= keep_bits(x.z); d.w &= keep_bits(x.w);
+        }
         if (cok[i]) *reinterpret_cast<uint4*>(dst + cbase[i] + c0) = d;
       }
     }
@@ -892,7 +910,8 @@ __global__ void k_dy_top_bf16(const bf16* __restrict__ X, const float* __restric
   const int64_t bh = pix / H;
   const int h = (int)(bh % H);
   const int64_t b = bh / H;
-  const float m = __bfloat162float(X[e]) > 0.f ? phi_scale<ACT>() : 0.f;
+  // (gelu: X points at the stored derivative phi'(Y))
+  const float m = ACT == CFFM_ACT_GELU ? __bfloat162float(X[e]) : (__bfloat162float(X[e]) > 0.f ? phi_scale<ACT>() : 0.f);
   const float v = gout[b] * v_lvl[h] * m;
   const bf16 hi = __float2bfloat16_rn(v);
   dY[e] = hi;
@@ -926,6 +945,7 @@ struct TCState {
   int64_t wg_partial_floats = 0;
   float* bg_partial = nullptr;   // bias-gradient chunk scratch [64][P]
   float* pool_part = nullptr;    // forward layers >= 1: pooled sums per N tile [tiles_n][B * K/4]
+  bf16* Dphi[kMaxConv + 1] = {}; // gelu, training: phi'(Y_{l-1}) in the layout of X[l]
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
   bf16* Wf0lo = nullptr;         // split mode: their lo halves
   bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
@@ -954,8 +974,8 @@ static int tcmalloc(Model* m, T** p, int64_t n) {
 #define TCTRY(x) do { int _r = (x); if (_r != CFFM_OK) return _r; } while (0)
 
 // Scoring (forward only) runs on the tensor cores for outer_dims 16 / 32 / 64 and every activation (the sweep of
-// BASELINE.json configs[4]); training needs outer_dims == 32 and an activation whose derivative follows from the stored
-// post-activation (tc_train_supported).
+// BASELINE.json configs[4]); training needs outer_dims == 32; gelu, whose derivative does not follow from the stored
+// post-activation, trains in bf16 mode with its derivative stored beside the activations (tc_train_supported).
 int tc_supported(Model* m) {
   if (!m->cfg.outer_conv) return CFFM_OK;
   if (m->Ko != 16 && m->Ko != 32 && m->Ko != 64) { m->err = "tensor-core precisions need outer_dims 16, 32 or 64 (other sizes run in fp32)"; return CFFM_ERR_UNSUPPORTED; }
@@ -968,7 +988,10 @@ int tc_supported(Model* m) {
 int tc_train_supported(Model* m) {
   if (!m->cfg.outer_conv) return CFFM_OK;
   if (m->Ko != 32) { m->err = "training in a tensor-core precision needs outer_dims == 32 (16 / 64: scoring only; train in fp32)"; return CFFM_ERR_UNSUPPORTED; }
-  if (m->cfg.activation == CFFM_ACT_GELU) { m->err = "training in a tensor-core precision does not support gelu (its derivative needs the pre-activation); scoring does"; return CFFM_ERR_UNSUPPORTED; }
+  if (m->cfg.activation == CFFM_ACT_GELU && m->cfg.precision != CFFM_PREC_BF16) {
+    m->err = "gelu trains in fp32 or bf16 (bf16 stores its derivative in bf16 beside the activations; the split mode does not)";
+    return CFFM_ERR_UNSUPPORTED;
+  }
   return CFFM_OK;
 }
 
@@ -997,7 +1020,9 @@ int tc_alloc(Model* m, bool train) {
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
     // (split mode: the forward kernel splits its intermediate Z into hi + lo as well; the factorised data and weight
     // gradients round their intermediates to bf16 and are not used, layer 0's backward stays in the direct form)
-    if (m->Ko == 32 && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) && !(f0 && !strcmp(f0, "direct"))) {
+    // (gelu keeps layer 0 in the direct form: only the k_tc epilogues store the derivative it trains with)
+    if (m->Ko == 32 && m->cfg.activation != CFFM_ACT_GELU && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) &&
+        !(f0 && !strcmp(f0, "direct"))) {
       st->KA = (2 * m->F + 15) & ~15; st->nblk = st->KA > 64 ? 2 : 1; st->Q16 = (m->P + 15) & ~15;
       const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
       TCTRY(tcmalloc(m, &st->Wf0, n));
@@ -1017,6 +1042,8 @@ int tc_alloc(Model* m, bool train) {
     for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dY[l], B * H * H * Pp)); }
     if (st->split)
       for (int l = 0; l < m->n_live; ++l) { const int64_t H = m->Ko >> (l + 1); TCTRY(tcmalloc(m, &st->dYlo[l], B * H * H * Pp)); }
+    if (m->cfg.activation == CFFM_ACT_GELU)
+      for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->Dphi[l], B * H * H * Pp)); }
     // split factor of the largest weight gradient decides the scratch size
     const int tiles = (4 * st->Pp / BM) * (st->Pp / st->BN);
     int max_split = (2 * 148 + tiles - 1) / tiles; if (max_split < 1) max_split = 1;
@@ -1044,7 +1071,7 @@ int tc_alloc(Model* m, bool train) {
 void tc_free(Model* m) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   if (!st) return;
-  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) dev_free(st->X[l]); if (st->Xlo[l]) dev_free(st->Xlo[l]); }
+  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) dev_free(st->X[l]); if (st->Xlo[l]) dev_free(st->Xlo[l]); if (st->Dphi[l]) dev_free(st->Dphi[l]); }
   for (int l = 0; l < kMaxConv; ++l) {
     if (st->dY[l]) dev_free(st->dY[l]); if (st->Wt[l]) dev_free(st->Wt[l]); if (st->Wd[l]) dev_free(st->Wd[l]);
     if (st->dYlo[l]) dev_free(st->dYlo[l]); if (st->Wtlo[l]) dev_free(st->Wtlo[l]); if (st->Wdlo[l]) dev_free(st->Wdlo[l]);
@@ -1214,7 +1241,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
       }
       p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j; p.pool_part = nullptr;
-      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[1];
+      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[1]; p.Dphi = st->Dphi[1];
       memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g0.BN, 64));
       if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[0], Pp, 4 * Pp, g0.BN, 64));
@@ -1223,7 +1250,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
       ConvFwdTC<ACT, false, SPLIT> p;
       p.g = g; p.bias = m->dense_w + m->lay.conv_b[l]; p.Xout = st->X[l + 1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr; p.pool_part = st->pool_part;
-      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[l + 1];
+      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[l + 1]; p.Dphi = st->Dphi[l + 1];
       memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
       TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[l], Pp, 4 * Pp, g.BN, 64));
@@ -1262,7 +1289,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
     const int H = K >> (l + 1);
     const int64_t total = (int64_t)B * H * H * Pp;
     CFFM_PROF(m, "dy_top", s);
-    k_dy_top_bf16<ACT><<<ceil_div(total, 256), 256, 0, s>>>(st->X[l + 1], m->gout, m->v_head + lvl_off[l + 1], H, Pp, total, st->dY[l],
+    k_dy_top_bf16<ACT><<<ceil_div(total, 256), 256, 0, s>>>(ACT == CFFM_ACT_GELU ? st->Dphi[l + 1] : st->X[l + 1], m->gout, m->v_head + lvl_off[l + 1], H, Pp, total, st->dY[l],
                                                             st->dYlo[l]);
     m->launches++;
   }
@@ -1374,7 +1401,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         TCTRY(launch_tc(m, p, B, s));
       } else {
         ConvDgradTC<ACT, SPLIT> p;
-        p.g = gd; p.X = st->X[l]; p.dYprev = st->dY[l - 1]; p.gout = m->gout; p.v_head = m->v_head; p.sp_off = lvl_off[l];
+        p.g = gd; p.X = ACT == CFFM_ACT_GELU ? st->Dphi[l] : st->X[l]; p.dYprev = st->dY[l - 1]; p.gout = m->gout; p.v_head = m->v_head; p.sp_off = lvl_off[l];
         p.sk.nparts = st->split ? 3 : 1; p.dYprev_lo = st->dYlo[l - 1];
         memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[l], rows, Pp, BM, 64));

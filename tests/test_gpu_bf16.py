@@ -141,14 +141,46 @@ def test_bf16_training_tracks_fp32():
     assert abs(res["fp32"] - res["bf16"]) < 0.07, res
 
 
+@pytest.mark.parametrize("F,M,B", [(10, 400, 24), (20, 700, 9)])
+def test_bf16_gelu_trains(F, M, B):
+    """gelu (CFFM.py:149-151): phi'(y) = Phi(r) + r N(r) does not follow from the sign of the stored activation, so the
+    forward epilogues store it (bf16) next to X and the data gradient multiplies by it instead of masking."""
+    from cffm_b200 import Engine
+    from oracle.cffm_ref import CFFMRef
+    rng = np.random.default_rng(5)
+    eng = Engine(M, F, 32, 32, activation="gelu", max_batch=B, precision="bf16", seed=3)
+    eng.set_param("feature_bias", rng.normal(0, 0.05, (M, 1)).astype(np.float32))
+    eng.set_param("outer_embeddings", rng.normal(0, 0.3, (M, 32)).astype(np.float32))
+    P = F * (F - 1) // 2
+    for l in range(5):
+        eng.set_param("outer_layer_conv_weight_%d" % l, rng.normal(0, 1.0 / np.sqrt(4 * P), (2, 2, P, P)).astype(np.float32))
+    ref = CFFMRef(M, F, 32, 32, activation="gelu", dtype=torch.float64)
+    for k, v in eng.get_weights().items():
+        ref.params[k] = torch.from_numpy(v.astype(np.float64)).reshape(ref.params[k].shape)
+    ids = rng.integers(0, M, (B, F)).astype(np.int32)
+    y = rng.choice([-1.0, 1.0], B).astype(np.float32)
+    assert _rel(eng.forward(ids), ref.predict(ids).numpy()) < 1e-2
+    l_ref, dense, sparse = ref.gradients(ids, y)
+    loss = eng.train_step(ids, y)
+    assert abs(loss - float(l_ref)) < 1e-2 * max(1.0, float(l_ref))
+    errs = {}
+    for l in range(4):
+        errs["wgrad%d" % l] = _rel2(eng.dense_grad("outer_layer_conv_weight_%d" % l), dense["outer_layer_conv_weight_%d" % l].numpy())
+    errs["outer_rows"] = _rel2(eng.fetch("grad_outer_rows"), sparse["outer_embeddings"][2].numpy())
+    print("gelu", F, {k: round(v, 4) for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if v > (0.12 if k == "wgrad3" else 5e-2)}
+    assert not bad, errs
+    eng.close()
+
+
 def test_bf16_rejects_what_it_cannot_do():
     """Scoring runs on the tensor cores for outer_dims 16 / 32 / 64 and every activation; TRAINING there needs
     outer_dims == 32 and an activation whose derivative follows from the stored post-activation."""
     from cffm_b200 import Engine, CffmError
     ids = np.zeros((4, 4), dtype=np.int32)
     y = np.ones(4, dtype=np.float32)
-    for kw in (dict(inner_dims=16, outer_dims=16), dict(inner_dims=32, outer_dims=32, activation="gelu")):
-        eng = Engine(100, 4, max_batch=4, precision="bf16", **kw)
+    for prec, kw in (("bf16", dict(inner_dims=16, outer_dims=16)), ("bf16x3", dict(inner_dims=32, outer_dims=32, activation="gelu"))):
+        eng = Engine(100, 4, max_batch=4, precision=prec, **kw)
         assert eng.forward(ids).shape == (4,)
         with pytest.raises(CffmError):
             eng.train_step(ids, y)

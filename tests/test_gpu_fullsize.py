@@ -93,3 +93,52 @@ def test_criteo_shape_properties():
     loss2 = eng2.train_step(ids, y)
     assert loss2 == loss                                                     # run-to-run determinism
     eng.close(); eng2.close()
+
+
+@pytest.mark.timeout(580)
+@pytest.mark.parametrize("precision,layer0", [("bf16", "factorised"), ("bf16", "direct"), ("bf16x3", "factorised"), ("fp32", "direct")])
+def test_criteo_field_count_gradients_vs_oracle(precision, layer0, monkeypatch):
+    """F = 39 (741 pairs, 768 padded channels, three N tiles) with a batch that spans several 8-sample tiles and partial
+    ones (B = 44): logits, every conv gradient and the embedding-row gradients against the fp64 oracle -- the gradient
+    comparison at the Criteo field count that the B = 6 parity case is too small for."""
+    from cffm_b200 import Engine
+    from oracle.cffm_ref import CFFMRef
+    if layer0 == "factorised":
+        monkeypatch.setenv("CFFM_FACT_MIN_BATCH", "1"); monkeypatch.setenv("CFFM_FACT_MIN_FIELDS", "1")
+    else:
+        monkeypatch.setenv("CFFM_FACT_MIN_BATCH", "1000000000")
+    F, K, M, B = 39, 32, 3000, 44
+    rng = np.random.default_rng(11)
+    eng = Engine(M, F, K, K, activation="relu", max_batch=B, precision=precision, seed=3)
+    eng.set_param("feature_bias", rng.normal(0, 0.05, (M, 1)).astype(np.float32))
+    eng.set_param("outer_embeddings", rng.normal(0, 0.3, (M, K)).astype(np.float32))
+    P = F * (F - 1) // 2
+    for l in range(5):
+        eng.set_param("outer_layer_conv_weight_%d" % l, rng.normal(0, 1 / np.sqrt(4 * P), (2, 2, P, P)).astype(np.float32))
+    ref = _oracle_from(eng, M, F, "relu")
+    ids = rng.integers(0, M, (B, F)).astype(np.int32)
+    ids[:, 0] = ids[:, 0] % 5                     # heavy duplication in one field
+    y = rng.choice([-1.0, 1.0], B).astype(np.float32)
+    tol = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 1e-2}[precision]
+    out = eng.forward(ids)
+    assert _rel(out, ref.predict(ids).numpy()) < tol
+    l_ref, dense, sparse = ref.gradients(ids, y)
+    loss = eng.train_step(ids, y)
+    assert abs(loss - float(l_ref)) < tol * max(1.0, float(l_ref))
+
+    def rel2(a, b):
+        a = np.asarray(a, np.float64).reshape(-1); b = np.asarray(b, np.float64).reshape(-1)
+        return float(np.linalg.norm(a - b) / max(1e-30, np.linalg.norm(b)))
+    gtol = {"fp32": 1e-3, "bf16x3": 5e-3, "bf16": 5e-2}[precision]
+    errs = {}
+    for l in range(4):
+        errs["wgrad%d" % l] = rel2(eng.dense_grad("outer_layer_conv_weight_%d" % l), dense["outer_layer_conv_weight_%d" % l].numpy())
+        errs["bgrad%d" % l] = rel2(eng.dense_grad("outer_layer_conv_bias_%d" % l), dense["outer_layer_conv_bias_%d" % l].numpy())
+    errs["outer_rows"] = rel2(eng.fetch("grad_outer_rows"), sparse["outer_embeddings"][2].numpy())
+    errs["inner_rows"] = rel2(eng.fetch("grad_inner_rows"), sparse["inner_embeddings"][2].numpy())
+    errs["bias_rows"] = rel2(eng.fetch("grad_bias_rows"), sparse["feature_bias"][2].numpy())
+    print(precision, layer0, {k: "%.2e" % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if v > (0.12 if (precision == "bf16" and k.endswith("3")) else gtol)}
+    assert not bad, (precision, layer0, bad)
+    assert int(eng.fetch("n_uniq")[0]) == len(np.unique(ids))
+    eng.close()
