@@ -659,7 +659,7 @@ void launch_sparse_update(const SparseWork* w, const SparseTables& t, int64_t n,
   if (any_sparse) {
     launch_segment_sums(w, t, n, s, launches);
     const GSums G = gsums_of(w, t);
-    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+    int blocks = (int)((n * 32 + 255) / 256); if (blocks > 148 * 64) blocks = 148 * 64;   // a row per warp: many short chains
     if (maxc_of(t) == 2) k_apply_rows<2><<<blocks, 256, 0, s>>>(w->keys_out, w->seg_start, w->n_uniq, t, G, opt, lr, lr_dev);
     else k_apply_rows<1><<<blocks, 256, 0, s>>>(w->keys_out, w->seg_start, w->n_uniq, t, G, opt, lr, lr_dev);
     if (launches) *launches += 1;
