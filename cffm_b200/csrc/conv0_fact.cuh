@@ -45,13 +45,12 @@ static_assert(sizeof(F0Ctl) <= 256, "control block");
 static_assert(F0_SMEM <= 227 * 1024, "factorised forward exceeds the shared memory of an SM");
 // Split mode (CFFM_PREC_BF16X3): the A tile and every weight slab exist as hi and lo halves, Z is split into hi and
 // lo when it is converted (the two bf16 copies fill exactly the columns of the fp32 Z they are made from) and both
-// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of two stages
-// of (hi, lo) pairs (a third changed nothing).  The epilogue collects 8 channels instead of 16 and writes X_1 in the
-// split mode's interleaved layout -- per 8 channels 16 bytes of hi, then 16 bytes of lo -- so that a (row, w) of a
-// group is one full 32-byte sector: with separate hi / lo tensors the 16-byte rows cost 7 of the kernel's 12.5 ms
-// (ablation without stores: 5.3 ms) and wrote 11.7 GB for 6.4 GB of payload.
-constexpr int F0S_NST = 2;
-constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
+// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of THREE
+// stages of (hi, lo) pairs (two left the tensor pipe waiting: 2.6 us per channel against 0.85 us of MMAs), and the
+// epilogue collects 8 channels instead of 16; its hi and lo tiles go through ONE 4 KB staging tile per warp, one
+// after the other (that is what makes room for the third stage).
+constexpr int F0S_NST = 3;
+constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * (F0_STAGE_BYTES / 2) + 128;
 static_assert(F0S_SMEM <= 227 * 1024, "split-mode factorised forward exceeds the shared memory of an SM");
 
 struct Fwd0FactParams {
@@ -59,7 +58,7 @@ struct Fwd0FactParams {
   CUtensorMap mapX;     // X1 as (q: Pp, row = b*16+h: B*16, w: 16), dense box (16, 32, 8) for the epilogue's TMA stores
   CUtensorMap mapW2, mapX2;   // split mode: the lo halves (mapX / mapX2 then have box (8, 32, 8))
   bf16* Xout_lo;
-  int tma_store;        // 0: the tensor map could not be encoded, lanes store their sectors themselves; 2: ablation, no stores
+  int tma_store;        // 0: the tensor map could not be encoded, lanes store their sectors themselves
   const float* rows;    // outer rows [B][F][32]
   const float* bias;
   bf16* Xout;           // X1 [B][16][16][Pp]
@@ -123,7 +122,7 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
   constexpr int SLAB_STAGE = (SPLIT ? 2 : 1) * F0_SLAB_BYTES;           // one stage: the slab (hi) [+ its lo half]
   constexpr int AT_BYTES = (SPLIT ? 4 : 2) * A_STAGE_BYTES;             // A tile: [hi: nblk blocks][lo: nblk blocks]
   constexpr int QG = SPLIT ? 8 : 16;                                    // channels an epilogue thread collects per store
-  constexpr int WARP_STAGE = F0_STAGE_BYTES;                            // staging tile of an epilogue warp
+  constexpr int WARP_STAGE = SPLIT ? F0_STAGE_BYTES / 2 : F0_STAGE_BYTES;  // staging tile of an epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B] (split: hi at 0, lo at 2 * A_STAGE_BYTES)
@@ -358,24 +357,26 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
             } else prev[w] = x;
           }
         }
-        if (prm.tma_store == 2) {
-          // ablation switch (CFFM_F0_TMASTORE=skip): results are dropped -- measures what the stores cost
-        } else if (prm.tma_store) {
+        if (prm.tma_store) {
           // 32 rows x 8 w x QG channels of this warp -> staging tile -> one TMA store (rows beyond the batch are
           // clipped by the tensor map); the copy engine does the scattered 32-byte writes, not the LSU
           if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
           __syncwarp();
           if constexpr (SPLIT) {
-            // interleaved X_1: [8 hi | 8 lo] of this 8-channel group = one 32-byte sector per (row, w)
+            // hi tile, its store, then the lo tile through the same 4 KB
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-              uint4* d = reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 32);
-              d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
-              d[1] = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
-            }
+            for (int w = 0; w < 8; ++w)
+              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) tma_store_3d(&prm.mapX, stage, 2 * q0, tile * BM + qd * 32, grp * 8);
+            if (lane == 0) { tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8); tma_store_wait_read(); }
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_3d(&prm.mapX2, stage, q0, tile * BM + qd * 32, grp * 8);
           } else {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -392,8 +393,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
             if constexpr (SPLIT) {
-              const uint32_t r8[8] = {acc[w][0], acc[w][1], acc[w][2], acc[w][3], accl[w][0], accl[w][1], accl[w][2], accl[w][3]};
-              st_global_256(prm.Xout + 2 * (off + (int64_t)w * prm.Pp), r8);   // (off counts plain elements; q0 is a multiple of 8)
+              *reinterpret_cast<uint4*>(prm.Xout + off + (int64_t)w * prm.Pp) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+              *reinterpret_cast<uint4*>(prm.Xout_lo + off + (int64_t)w * prm.Pp) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
             } else {
               uint32_t r8[8];
 #pragma unroll

@@ -86,7 +86,6 @@ struct ConvFwdTC : KMajorA, KMajorB {
   CUtensorMap mapA, mapB, mapA2, mapB2;   // *2: the lo halves (split mode)
   Geom g;
   SplitK sk; bf16* Xout_lo;
-  int a_inter;              // split mode, layer 1: the A operand (X_1) is stored hi / lo interleaved (see im2col_map_inter)
   bf16* Dphi;               // gelu, training: phi'(Y) next to X = phi(Y) (its derivative does not follow from X's sign)
   const float* bias; bf16* Xout; float* t1; int t1_dim, sp_off;
   float* pool_part;         // l >= 1, tiles_n > 1: pooled sums per N tile [tiles_n][B*Ho], added up by k_pool_parts
@@ -121,8 +120,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
     const int m0 = un.m_tile * BM;
     const int b0 = m0 >> (2 * g.lgHo), h0 = (m0 >> g.lgHo) & (g.Ho - 1);
     const int k0 = sk.base(kc) * BK, dh = k0 / (2 * g.Pp), c0 = k0 - dh * 2 * g.Pp;
-    if (a_inter) tma_load_5d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, 0, c0 >> 3, 0, dh, b0 * g.Ho + h0);
-    else tma_load_5d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, c0, 0, dh, h0, b0);
+    tma_load_5d(s, sk.a_lo(kc) ? &mapA2 : &mapA, bar, c0, 0, dh, h0, b0);
   }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
     tma_load_2d(s, sk.b_lo(kc) ? &mapB2 : &mapB, bar, sk.base(kc) * BK, un.n_tile * g.BN);
@@ -237,17 +235,7 @@ struct ConvFwdTC : KMajorA, KMajorB {
         if constexpr (SPLIT) pl[j >> 1] = pack2_lo(x0, x1);
         if constexpr (ACT == CFFM_ACT_GELU) pd[j >> 1] = pack2(phi_df<ACT>(y0), phi_df<ACT>(y1));
       }
-      if constexpr (L0 && SPLIT) {
-        // X_1 of the split mode is stored interleaved: per 8 channels 16 bytes of hi, then 16 bytes of lo (one sector)
-        if (m < p.g.M) {
-          uint4* dst = reinterpret_cast<uint4*>(p.Xout + (int64_t)m * 2 * p.g.Pp + (n0 >> 3) * 16);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            dst[2 * q4] = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-            dst[2 * q4 + 1] = make_uint4(pl[4 * q4], pl[4 * q4 + 1], pl[4 * q4 + 2], pl[4 * q4 + 3]);
-          }
-        }
-      } else if (m < p.g.M) {
+      if (m < p.g.M) {
         uint4* dst = reinterpret_cast<uint4*>(p.Xout + (int64_t)m * p.g.Pp + n0);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
@@ -311,7 +299,6 @@ struct ConvDgradTC : KMajorA, KMajorB {
   CUtensorMap mapA, mapB, mapA2, mapB2;   // A: dY_l dims (Pp, M) box (64,128); B: Wd dims (Pp, 4Pp) box (64, BN); *2: lo halves
   Geom g;                   // BN divides Pp; tiles_n = 4*Pp/BN
   SplitK sk; bf16* dYprev_lo;
-  int x_inter;              // split mode, layer 1: X_1 (the mask source) is stored hi / lo interleaved
   const bf16* X; bf16* dYprev; const float* gout; const float* v_head; int sp_off;
   __device__ uint32_t idesc() const { return umma_idesc_bf16(BM, g.BN); }
   __device__ int bn() const { return g.BN; }
@@ -343,7 +330,6 @@ struct ConvDgradTC : KMajorA, KMajorB {
     const ConvDgradTC& p; int row, sub, lane; float dsp;
     uint8_t* stg;
     int64_t cbase[4]; bool cok[4];   // rows (lane>>2) + 8i of this warp's 32: element offset of this lane's 8 channels
-    int64_t xbase[SPLIT ? 4 : 1];    // split mode: the same for the mask source when it is stored interleaved
     // split mode: three times the MMA time per unit covers the drain, and the lo halves double its register need:
     // the mask is then fetched chunk by chunk instead of for the whole unit ahead of the accumulator
     uint4 mk[SPLIT ? 1 : MAX_BN / 64][4];
@@ -364,9 +350,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
         const int m = un.m_tile * BM + (row & ~31) + (lane >> 2) + 8 * i;
         cok[i] = m < p.g.M;
         int b, h, w; p.g.pos(cok[i] ? m : 0, b, h, w);
-        const int64_t pix = ((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw;
-        cbase[i] = pix * p.g.Pp + pb + (lane & 3) * 8;
-        if constexpr (SPLIT) xbase[i] = p.x_inter ? pix * 2 * p.g.Pp + (int64_t)((pb >> 3) + (lane & 3)) * 16 : cbase[i];
+        cbase[i] = (((int64_t)b * p.g.Hin + 2 * h + dh) * p.g.Hin + 2 * w + dw) * p.g.Pp + pb + (lane & 3) * 8;
       }
       if constexpr (!SPLIT) {
 #pragma unroll
@@ -392,7 +376,7 @@ struct ConvDgradTC : KMajorA, KMajorB {
       if constexpr (SPLIT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          mk[0][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + xbase[i] + (p.x_inter ? (c0 >> 3) * 16 : c0))) : make_uint4(0u, 0u, 0u, 0u);
+          mk[0][i] = cok[i] ? __ldg(reinterpret_cast<const uint4*>(p.X + cbase[i] + c0)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) o[j >> 1] = pack2((v[j] + dsp) * phi_scale<ACT>(), (v[j + 1] + dsp) * phi_scale<ACT>());
@@ -639,7 +623,6 @@ struct ConvWgradTC : KMajorA, MNMajorB {
   CUtensorMap mapA, mapB, mapA2, mapB2;   // A (l>=1): 5-D im2col map, box = 64 channels x 64 positions; B: dY dims (Pp, M) box (64,64); *2: lo halves
   Geom g;                   // BN divides Pp, multiple of 64
   SplitK sk;
-  int a_inter;              // split mode, layer 1: X_1 stored hi / lo interleaved
   int chunks_total, chunks_per_split, n_split;
   float* partial;
   const float* rows; const int* pair_i; const int* pair_j;
@@ -677,8 +660,7 @@ struct ConvWgradTC : KMajorA, MNMajorB {
     for (int i = 0; i < 2; ++i) {
       const int kk0 = (un.m_tile * (kRows / 64) + i) * 64;
       const int dh = kk0 / (2 * g.Pp), c0 = kk0 - dh * 2 * g.Pp;
-      if (a_inter) tma_load_5d(s + i * 8192, map, bar, 0, c0 >> 3, 0, dh, b0 * g.Ho + h0);
-      else tma_load_5d(s + i * 8192, map, bar, c0, 0, dh, h0, b0);
+      tma_load_5d(s + i * 8192, map, bar, c0, 0, dh, h0, b0);
     }
   }
   __device__ void load_b(uint8_t* s, uint64_t* bar, Unit un, int kc) const {
@@ -1024,12 +1006,10 @@ int tc_alloc(Model* m, bool train) {
     st->BN = pick_bn(st->Pp);
     st->split = m->cfg.precision == CFFM_PREC_BF16X3;
     const int64_t B = m->max_batch, Pp = st->Pp;
-    // (split mode: X_1 holds hi and lo interleaved per 8 channels, Xlo[1] is the view 8 elements in)
-    for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp * ((st->split && l == 1) ? 2 : 1))); }
+    for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->X[l], B * H * H * Pp)); }
     for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wt[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wd[l], 4 * Pp * Pp)); }
     if (st->split) {
-      st->Xlo[1] = st->X[1] + 8;
-      for (int l = 2; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->Xlo[l], B * H * H * Pp)); }
+      for (int l = 1; l <= m->n_live; ++l) { const int64_t H = m->Ko >> l; TCTRY(tcmalloc(m, &st->Xlo[l], B * H * H * Pp)); }
       for (int l = 0; l < m->n_live; ++l) { TCTRY(tcmalloc(m, &st->Wtlo[l], 4 * Pp * Pp)); TCTRY(tcmalloc(m, &st->Wdlo[l], 4 * Pp * Pp)); }
     }
     TCTRY(tcmalloc(m, &st->pool_part, (Pp / st->BN) * B * (m->Ko >> 2)));
@@ -1048,10 +1028,11 @@ int tc_alloc(Model* m, bool train) {
       TCTRY(tcmalloc(m, &st->Wf0, n));
       CFFM_CUDA_OK(m, cudaMemset(st->Wf0, 0, sizeof(bf16) * (size_t)n));
       // channels Q16..Pp-1 of X1 are never written by that kernel
-      CFFM_CUDA_OK(m, cudaMemset(st->X[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp * (st->split ? 2 : 1))));
+      CFFM_CUDA_OK(m, cudaMemset(st->X[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
       if (st->split) {
         TCTRY(tcmalloc(m, &st->Wf0lo, n));
         CFFM_CUDA_OK(m, cudaMemset(st->Wf0lo, 0, sizeof(bf16) * (size_t)n));
+        CFFM_CUDA_OK(m, cudaMemset(st->Xlo[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
       }
     }
   }
@@ -1090,11 +1071,7 @@ int tc_alloc(Model* m, bool train) {
 void tc_free(Model* m) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   if (!st) return;
-  for (int l = 0; l <= kMaxConv; ++l) {
-    if (st->X[l]) dev_free(st->X[l]);
-    if (st->Xlo[l] && l != 1) dev_free(st->Xlo[l]);      // Xlo[1] is a view into X[1]
-    if (st->Dphi[l]) dev_free(st->Dphi[l]);
-  }
+  for (int l = 0; l <= kMaxConv; ++l) { if (st->X[l]) dev_free(st->X[l]); if (st->Xlo[l]) dev_free(st->Xlo[l]); if (st->Dphi[l]) dev_free(st->Dphi[l]); }
   for (int l = 0; l < kMaxConv; ++l) {
     if (st->dY[l]) dev_free(st->dY[l]); if (st->Wt[l]) dev_free(st->Wt[l]); if (st->Wd[l]) dev_free(st->Wd[l]);
     if (st->dYlo[l]) dev_free(st->dYlo[l]); if (st->Wtlo[l]) dev_free(st->Wtlo[l]); if (st->Wdlo[l]) dev_free(st->Wdlo[l]);
@@ -1131,19 +1108,6 @@ static bool im2col_map(const TCState* st, CUtensorMap* map, const bf16* X, int B
   const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bb};
   return st->enc.encode_bf16(map, const_cast<bf16*>(X), 5, dims, str, box);
 }
-// The same view of X_1 in the split mode's interleaved layout: a pixel row holds 2*Pp elements, per 8 channels 8 hi then
-// 8 lo values (the layer-0 forward then stores whole 32-byte sectors).  One part (hi: base X, lo: base X + 8) seen as
-// (c_in = 8, g = (dw, p / 8) [stride 16], w, dh, hb = (b, h) merged: the b stride is Ho times the h stride); the box
-// (8, 8, bw, 1, rows / bw) lands in shared memory exactly like the 64-channel box of the plain layout.
-static bool im2col_map_inter(const TCState* st, CUtensorMap* map, const bf16* Xpart, int B, int Hin, int Pp, int rows) {
-  const int Ho = Hin / 2;
-  const uint64_t row = (uint64_t)2 * Pp * 2;   // bytes of one pixel (hi + lo)
-  const uint64_t dims[5] = {8, (uint64_t)2 * Pp / 8, (uint64_t)Ho, 2, (uint64_t)B * Ho};
-  const uint64_t str[4] = {32, 2 * row, (uint64_t)Hin * row, (uint64_t)2 * Hin * row};
-  int bw = Ho, bhb = rows / bw; if (bhb < 1) bhb = 1;
-  const uint32_t box[5] = {8, 8, (uint32_t)bw, 1, (uint32_t)bhb};
-  return st->enc.encode_bf16(map, const_cast<bf16*>(Xpart), 5, dims, str, box);
-}
 static bool mat_map(const TCState* st, CUtensorMap* map, const bf16* X, int64_t rows, int cols, int box_rows, int box_cols) {
   const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
   const uint64_t str[1] = {(uint64_t)cols * 2};
@@ -1175,16 +1139,14 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapW2, 0, sizeof(p.mapW2)); memset(&p.mapX2, 0, sizeof(p.mapX2));
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
   if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapW2, st->Wf0lo, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
-  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16, 32, 8) TMA stores; split mode: a pixel row is
-     // 2*Pp elements (8 hi, 8 lo per 8 channels) and a box covers the 16 elements = one sector of an 8-channel group
-    const uint64_t rowel = (uint64_t)st->Pp * (SPLIT ? 2 : 1);
-    const uint64_t dims[3] = {rowel, (uint64_t)B * 16, 16};
-    const uint64_t str[2] = {(uint64_t)16 * rowel * 2, rowel * 2};
-    const uint32_t box[3] = {16, 32, 8};
+  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16 | 8, 32, 8) TMA stores
+    const uint64_t dims[3] = {(uint64_t)st->Pp, (uint64_t)B * 16, 16};
+    const uint64_t str[2] = {(uint64_t)16 * st->Pp * 2, (uint64_t)st->Pp * 2};
+    const uint32_t box[3] = {SPLIT ? 8u : 16u, 32, 8};
     const char* e = getenv("CFFM_F0_TMASTORE");
     p.tma_store = !(e && !strcmp(e, "0")) && st->enc.encode_bf16(&p.mapX, st->X[1], 3, dims, str, box, false) ? 1 : 0;
+    if (p.tma_store && SPLIT) p.tma_store = st->enc.encode_bf16(&p.mapX2, st->Xlo[1], 3, dims, str, box, false) ? 1 : 0;
     if (!p.tma_store) { memset(&p.mapX, 0, sizeof(p.mapX)); memset(&p.mapX2, 0, sizeof(p.mapX2)); }
-    if (e && !strcmp(e, "skip")) p.tma_store = 2;
   }
   p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.Xout_lo = st->Xlo[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
@@ -1279,7 +1241,7 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
       }
       p.g = g0; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j; p.pool_part = nullptr;
-      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[1]; p.Dphi = st->Dphi[1]; p.a_inter = 0;
+      p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[1]; p.Dphi = st->Dphi[1];
       memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[0], Pp, 4 * Pp, g0.BN, 64));
       if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[0], Pp, 4 * Pp, g0.BN, 64));
@@ -1289,17 +1251,13 @@ static int conv_forward_act(Model* m, int B, cudaStream_t s) {
       p.g = g; p.bias = m->dense_w + m->lay.conv_b[l]; p.Xout = st->X[l + 1]; p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = off;
       p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr; p.pool_part = st->pool_part;
       p.sk.nparts = st->split ? 3 : 1; p.Xout_lo = st->Xlo[l + 1]; p.Dphi = st->Dphi[l + 1];
-      p.a_inter = (st->split && l == 1) ? 1 : 0;
       memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
-      if (p.a_inter) {
-        TC_MAP_OK(m, im2col_map_inter(st, &p.mapA, st->X[1], B, g.Hin, Pp, BM));
-        TC_MAP_OK(m, im2col_map_inter(st, &p.mapA2, st->Xlo[1], B, g.Hin, Pp, BM));
-      } else {
-        TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
-        if (st->split) TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, g.Hin, Pp, BM));
-      }
+      TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, g.Hin, Pp, BM));
       TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wt[l], Pp, 4 * Pp, g.BN, 64));
-      if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[l], Pp, 4 * Pp, g.BN, 64));
+      if (st->split) {
+        TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, g.Hin, Pp, BM));
+        TC_MAP_OK(m, mat_map(st, &p.mapB2, st->Wtlo[l], Pp, 4 * Pp, g.BN, 64));
+      }
       TCTRY(launch_tc(m, p, m_tiles * g.tiles_n, s));
       if (g.tiles_n > 1) {
         k_pool_parts<<<(B * g.Ho + 255) / 256, 256, 0, s>>>(st->pool_part, g.tiles_n, B, g.Ho, m->t1, m->t1_dim, off);
@@ -1396,7 +1354,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         ConvWgradTC<ACT, true, SPLIT> p;
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
         p.rows = m->outer_rows; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
-        p.sk.nparts = st->split ? 3 : 1; p.a_inter = 0;
+        p.sk.nparts = st->split ? 3 : 1;
         memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[0], rows, Pp, 64, 64));
         if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[0], rows, Pp, 64, 64));
@@ -1406,17 +1364,13 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
         p.rows = nullptr; p.pair_i = nullptr; p.pair_j = nullptr;
         p.sk.nparts = st->split ? 3 : 1;
-        p.a_inter = (st->split && l == 1) ? 1 : 0;
         memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
-        if (p.a_inter) {
-          TC_MAP_OK(m, im2col_map_inter(st, &p.mapA, st->X[1], B, gm.Hin, Pp, 64));
-          TC_MAP_OK(m, im2col_map_inter(st, &p.mapA2, st->Xlo[1], B, gm.Hin, Pp, 64));
-        } else {
-          TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, gm.Hin, Pp, 64));
-          if (st->split) TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, gm.Hin, Pp, 64));
-        }
+        TC_MAP_OK(m, im2col_map(st, &p.mapA, st->X[l], B, gm.Hin, Pp, 64));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[l], rows, Pp, 64, 64));
-        if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[l], rows, Pp, 64, 64));
+        if (st->split) {
+          TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, gm.Hin, Pp, 64));
+          TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[l], rows, Pp, 64, 64));
+        }
         TCTRY(launch_tc(m, p, tiles * n_split, s));
       }
       if (!(l == 0 && st->wf_part && B >= st->fact_min_batch)) {
@@ -1448,7 +1402,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       } else {
         ConvDgradTC<ACT, SPLIT> p;
         p.g = gd; p.X = ACT == CFFM_ACT_GELU ? st->Dphi[l] : st->X[l]; p.dYprev = st->dY[l - 1]; p.gout = m->gout; p.v_head = m->v_head; p.sp_off = lvl_off[l];
-        p.sk.nparts = st->split ? 3 : 1; p.dYprev_lo = st->dYlo[l - 1]; p.x_inter = (st->split && l == 1) ? 1 : 0;
+        p.sk.nparts = st->split ? 3 : 1; p.dYprev_lo = st->dYlo[l - 1];
         memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->dY[l], rows, Pp, BM, 64));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->Wd[l], 4 * Pp, Pp, gd.BN, 64));
@@ -1495,17 +1449,11 @@ int tc_conv_backward(Model* m, int B, cudaStream_t s) {
 }
 
 // debug access for the parity tests: X_{l+1} = phi(Y_l) converted to fp32 [B,Ho,Ho,P]
-__global__ void k_unpad_bf16(const bf16* __restrict__ X, const bf16* __restrict__ Xlo, int64_t rows, int P, int Pp, int inter,
-                             float* __restrict__ out) {
+__global__ void k_unpad_bf16(const bf16* __restrict__ X, const bf16* __restrict__ Xlo, int64_t rows, int P, int Pp, float* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows * P) return;
   const int64_t r = e / P; const int c = (int)(e - r * P);
-  if (inter) {   // split mode's X_1: per 8 channels 8 hi then 8 lo values
-    const int64_t o = r * 2 * Pp + (c >> 3) * 16 + (c & 7);
-    out[e] = __bfloat162float(X[o]) + __bfloat162float(X[o + 8]);
-  } else {
-    out[e] = __bfloat162float(X[r * Pp + c]) + (Xlo ? __bfloat162float(Xlo[r * Pp + c]) : 0.f);
-  }
+  out[e] = __bfloat162float(X[r * Pp + c]) + (Xlo ? __bfloat162float(Xlo[r * Pp + c]) : 0.f);
 }
 int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
@@ -1513,7 +1461,7 @@ int tc_debug_fetch(Model* m, bool grad, int l, float* dev_out, int64_t rows) {
   const bf16* src = grad ? st->dY[l] : st->X[l + 1];
   const bf16* src_lo = grad ? st->dYlo[l] : st->Xlo[l + 1];
   if (!src) return CFFM_ERR_INVALID;
-  k_unpad_bf16<<<ceil_div(rows * m->P, 256), 256>>>(src, src_lo, rows, m->P, st->Pp, (!grad && l == 0 && st->split) ? 1 : 0, dev_out);
+  k_unpad_bf16<<<ceil_div(rows * m->P, 256), 256>>>(src, src_lo, rows, m->P, st->Pp, dev_out);
   return cudaDeviceSynchronize() == cudaSuccess ? CFFM_OK : CFFM_ERR_CUDA;
 }
 
