@@ -45,12 +45,15 @@ static_assert(sizeof(F0Ctl) <= 256, "control block");
 static_assert(F0_SMEM <= 227 * 1024, "factorised forward exceeds the shared memory of an SM");
 // Split mode (CFFM_PREC_BF16X3): the A tile and every weight slab exist as hi and lo halves, Z is split into hi and
 // lo when it is converted (the two bf16 copies fill exactly the columns of the fp32 Z they are made from) and both
-// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of THREE
-// stages of (hi, lo) pairs (two left the tensor pipe waiting: 2.6 us per channel against 0.85 us of MMAs), and the
-// epilogue collects 8 channels instead of 16; its hi and lo tiles go through ONE 4 KB staging tile per warp, one
-// after the other (that is what makes room for the third stage).
-constexpr int F0S_NST = 3;
-constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * (F0_STAGE_BYTES / 2) + 128;
+// steps issue three MMAs per K step: hi*hi + lo*hi + hi*lo.  Shared memory: A tile 2 x 32 KB, slab ring of two stages
+// of (hi, lo) pairs (a third changed nothing).  The epilogue collects 8 channels instead of 16 and writes them
+// INTERLEAVED -- per 8 channels 16 bytes of hi, then 16 bytes of lo -- into a scratch tensor X1i, so that a (row, w) of
+// a group is one full 32-byte sector; k_deinterleave_x1 then makes the separate hi / lo tensors the next layer's TMA
+// boxes want.  With 16-byte rows straight into the hi / lo tensors the stores cost 7 of the kernel's 12.5 ms (ablation
+// without stores: 5.3 ms) and wrote 11.7 GB for 6.4 GB of payload; reading the interleaved tensor with 16-byte TMA boxes
+// instead doubled the time of both layer-1 kernels.  The extra pass moves 12.8 GB (~2.2 ms).
+constexpr int F0S_NST = 2;
+constexpr int F0S_SMEM = 1024 + 4 * A_STAGE_BYTES + F0S_NST * 2 * F0_SLAB_BYTES + 256 + F0_BIAS_MAX * 4 + 2 * BM * 4 + 8 * F0_STAGE_BYTES + 128;
 static_assert(F0S_SMEM <= 227 * 1024, "split-mode factorised forward exceeds the shared memory of an SM");
 
 struct Fwd0FactParams {
@@ -116,13 +119,22 @@ __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restri
   }
 }
 
+// X1i [pixel][Pp / 8][hi8 | lo8] -> X1 hi [pixel][Pp], X1 lo [pixel][Pp]; a thread moves one 32-byte unit, neighbouring
+// threads write neighbouring 16-byte pieces of both outputs (full sectors on both sides)
+__global__ void k_deinterleave_x1(const uint4* __restrict__ Xi, int64_t units, uint4* __restrict__ Xhi, uint4* __restrict__ Xlo) {
+  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 h = __ldcs(Xi + 2 * u), l = __ldcs(Xi + 2 * u + 1);   // read once: streaming loads
+    Xhi[u] = h; Xlo[u] = l;
+  }
+}
+
 template <int ACT, bool SPLIT>
 __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_constant__ Fwd0FactParams prm) {
   constexpr int NST = SPLIT ? F0S_NST : F0_NST;                         // slab ring depth
   constexpr int SLAB_STAGE = (SPLIT ? 2 : 1) * F0_SLAB_BYTES;           // one stage: the slab (hi) [+ its lo half]
   constexpr int AT_BYTES = (SPLIT ? 4 : 2) * A_STAGE_BYTES;             // A tile: [hi: nblk blocks][lo: nblk blocks]
   constexpr int QG = SPLIT ? 8 : 16;                                    // channels an epilogue thread collects per store
-  constexpr int WARP_STAGE = SPLIT ? F0_STAGE_BYTES / 2 : F0_STAGE_BYTES;  // staging tile of an epilogue warp
+  constexpr int WARP_STAGE = F0_STAGE_BYTES;                            // staging tile of an epilogue warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAt = smem;                                   // [nblk][128 rows][128 B] (split: hi at 0, lo at 2 * A_STAGE_BYTES)
@@ -363,20 +375,16 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           if (lane == 0) tma_store_wait_read();     // the previous store has finished reading the tile
           __syncwarp();
           if constexpr (SPLIT) {
-            // hi tile, its store, then the lo tile through the same 4 KB
+            // interleaved scratch X1i: [8 hi | 8 lo] of this 8-channel group = one 32-byte sector per (row, w)
 #pragma unroll
-            for (int w = 0; w < 8; ++w)
-              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+            for (int w = 0; w < 8; ++w) {
+              uint4* d = reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 32);
+              d[0] = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+              d[1] = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { tma_store_3d(&prm.mapX, stage, q0, tile * BM + qd * 32, grp * 8); tma_store_wait_read(); }
-            __syncwarp();
-#pragma unroll
-            for (int w = 0; w < 8; ++w)
-              *reinterpret_cast<uint4*>(stage + (w * 32 + lane) * 16) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_3d(&prm.mapX2, stage, q0, tile * BM + qd * 32, grp * 8);
+            if (lane == 0) tma_store_3d(&prm.mapX, stage, 2 * q0, tile * BM + qd * 32, grp * 8);
           } else {
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -392,9 +400,9 @@ __global__ void __launch_bounds__(F0_THREADS, 1) k_fwd0_fact(const __grid_consta
           const int64_t off = (((int64_t)b * 16 + h) * 16 + grp * 8) * prm.Pp + q0;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
-            if constexpr (SPLIT) {
-              *reinterpret_cast<uint4*>(prm.Xout + off + (int64_t)w * prm.Pp) = make_uint4(acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
-              *reinterpret_cast<uint4*>(prm.Xout_lo + off + (int64_t)w * prm.Pp) = make_uint4(accl[w][0], accl[w][1], accl[w][2], accl[w][3]);
+            if constexpr (SPLIT) {   // Xout = the interleaved scratch X1i
+              const uint32_t r8[8] = {acc[w][0], acc[w][1], acc[w][2], acc[w][3], accl[w][0], accl[w][1], accl[w][2], accl[w][3]};
+              st_global_256(prm.Xout + 2 * (off + (int64_t)w * prm.Pp), r8);   // (off counts plain elements; q0 is a multiple of 8)
             } else {
               uint32_t r8[8];
 #pragma unroll

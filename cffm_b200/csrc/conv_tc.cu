@@ -948,6 +948,7 @@ struct TCState {
   bf16* Dphi[kMaxConv + 1] = {}; // gelu, training: phi'(Y_{l-1}) in the layout of X[l]
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
   bf16* Wf0lo = nullptr;         // split mode: their lo halves
+  bf16* X1i = nullptr;           // split mode: X_1 as the factorised forward writes it (hi / lo interleaved per 8 channels)
   bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
   float* df_bpart = nullptr;     // [tiles][4][Q16] column sums of dY0 collected by the factorised data gradient
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
@@ -1032,6 +1033,9 @@ int tc_alloc(Model* m, bool train) {
       if (st->split) {
         TCTRY(tcmalloc(m, &st->Wf0lo, n));
         CFFM_CUDA_OK(m, cudaMemset(st->Wf0lo, 0, sizeof(bf16) * (size_t)n));
+        const int64_t ni = 2 * B * (m->Ko >> 1) * (m->Ko >> 1) * Pp;
+        TCTRY(tcmalloc(m, &st->X1i, ni));
+        CFFM_CUDA_OK(m, cudaMemset(st->X1i, 0, sizeof(bf16) * (size_t)ni));   // channels Q16..Pp-1 are never written
         CFFM_CUDA_OK(m, cudaMemset(st->Xlo[1], 0, sizeof(bf16) * (size_t)(B * (m->Ko >> 1) * (m->Ko >> 1) * Pp)));
       }
     }
@@ -1081,6 +1085,7 @@ void tc_free(Model* m) {
   if (st->pool_part) dev_free(st->pool_part);
   if (st->Wf0) dev_free(st->Wf0);
   if (st->Wf0lo) dev_free(st->Wf0lo);
+  if (st->X1i) dev_free(st->X1i);
   if (st->Wf0T) dev_free(st->Wf0T);
   if (st->pterm0) dev_free(st->pterm0);
   if (st->df_bpart) dev_free(st->df_bpart);
@@ -1139,16 +1144,18 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapW2, 0, sizeof(p.mapW2)); memset(&p.mapX2, 0, sizeof(p.mapX2));
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
   if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapW2, st->Wf0lo, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
-  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16 | 8, 32, 8) TMA stores
-    const uint64_t dims[3] = {(uint64_t)st->Pp, (uint64_t)B * 16, 16};
-    const uint64_t str[2] = {(uint64_t)16 * st->Pp * 2, (uint64_t)st->Pp * 2};
-    const uint32_t box[3] = {SPLIT ? 8u : 16u, 32, 8};
+  bf16* xdst = SPLIT ? st->X1i : st->X[1];
+  {  // X1 seen as (q, row = b*16+h, w) for the epilogue's dense (16, 32, 8) TMA stores; split mode: the interleaved scratch,
+     // a pixel row is 2*Pp elements and a box covers the 16 elements [8 hi | 8 lo] of an 8-channel group
+    const uint64_t rowel = (uint64_t)st->Pp * (SPLIT ? 2 : 1);
+    const uint64_t dims[3] = {rowel, (uint64_t)B * 16, 16};
+    const uint64_t str[2] = {(uint64_t)16 * rowel * 2, rowel * 2};
+    const uint32_t box[3] = {16, 32, 8};
     const char* e = getenv("CFFM_F0_TMASTORE");
-    p.tma_store = !(e && !strcmp(e, "0")) && st->enc.encode_bf16(&p.mapX, st->X[1], 3, dims, str, box, false) ? 1 : 0;
-    if (p.tma_store && SPLIT) p.tma_store = st->enc.encode_bf16(&p.mapX2, st->Xlo[1], 3, dims, str, box, false) ? 1 : 0;
+    p.tma_store = !(e && !strcmp(e, "0")) && st->enc.encode_bf16(&p.mapX, xdst, 3, dims, str, box, false) ? 1 : 0;
     if (!p.tma_store) { memset(&p.mapX, 0, sizeof(p.mapX)); memset(&p.mapX2, 0, sizeof(p.mapX2)); }
   }
-  p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = st->X[1]; p.Xout_lo = st->Xlo[1];
+  p.rows = m->outer_rows; p.bias = m->dense_w + m->lay.conv_b[0]; p.Xout = xdst; p.Xout_lo = st->Xlo[1];
   p.t1 = m->t1; p.t1_dim = m->t1_dim; p.sp_off = sp_off;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
   constexpr int SMEM = SPLIT ? F0S_SMEM : F0_SMEM;
@@ -1161,6 +1168,12 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
   k_fwd0_fact<ACT, SPLIT><<<grid, F0_THREADS, SMEM, s>>>(p);
   m->launches++;
+  if (SPLIT) {   // interleaved scratch -> the separate hi / lo tensors of the next layer's TMA boxes
+    const int64_t units = (int64_t)B * 256 * st->Pp / 8;
+    k_deinterleave_x1<<<148 * 16, 256, 0, s>>>(reinterpret_cast<const uint4*>(st->X1i), units, reinterpret_cast<uint4*>(st->X[1]),
+                                              reinterpret_cast<uint4*>(st->Xlo[1]));
+    m->launches++;
+  }
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
 }
