@@ -208,7 +208,7 @@ def executed_flops(spec, tag, B, precision):
 
 
 FACT_WGRAD = True    # the layer-0 weight gradient runs in factorised form as well (conv0_wfact.cuh)
-SPLIT_FACT = ("conv_fwd_l0",)   # layer-0 kernels that run in factorised form in split (bf16x3) mode
+SPLIT_FACT = ("conv_fwd_l0", "conv_wgrad_l0")   # layer-0 kernels that run in factorised form in split (bf16x3) mode
 
 
 def ncu_traffic(spec, tag, B, precision):

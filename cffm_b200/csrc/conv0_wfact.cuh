@@ -8,6 +8,12 @@
 //   W step   dWq^T[n, k] += sum_{(b,h)} Et[n,(b,h)] A[(b,h), k]          TS MMA: Et converted to bf16 in place in TMEM,
 //                                                                        B = the A tile as MN-major B operand, K = 128
 // (E is produced transposed so that the contraction index of the second step runs along TMEM columns.)
+// The E step touches only the 16 x 16 block of a sample, so the dY0 blocks of a channel are kept compact: two 2 KB
+// regions of 16 rows (h) x 128 bytes, sample s of the tile in region s / 4 at byte columns 32 (s % 4) -- 4 KB per
+// channel instead of a 32 KB block-diagonal matrix.
+// Split mode (bf16x3): A8 and dY0 come as hi + lo; every product is hi*hi + lo*hi + hi*lo into the same fp32
+// accumulator (three MMAs), E^T is split into hi | lo bf16 halves of its own 64 TMEM columns, one builder group
+// places the hi blocks and the other the lo blocks of every tile.
 // The accumulators of 4 channels stay in TMEM while the CTA walks its share of the batch, so a unit is
 // (4 channels) x (a third of the tiles); CTAs that run at the same time hold neighbouring channel sets and read
 // the same 32-byte sectors of dY0 (L2 hits).  Partial sums per split are reduced in fixed order by k_wfact_reduce.
@@ -35,17 +41,21 @@ struct W0Ctl {
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(W0Ctl) <= 256, "control block");
-constexpr int W0_SMEM = 1024 + 2 * G0_DQ_BYTES + W0_ND * G0_DQ_BYTES + 256;
+constexpr int W0_DQC_BYTES = 4096;                          // compact dY0 blocks of one channel (8 samples x 16 x 16 bf16)
+constexpr int w0_smem(bool split) { return 1024 + (split ? 2 : 1) * (2 * G0_DQ_BYTES + W0_ND * W0_DQC_BYTES) + 256; }
+static_assert(w0_smem(true) <= 227 * 1024, "factorised weight gradient exceeds the shared memory of an SM");
 
 struct Wgrad0FactParams {
   CUtensorMap mapA;          // A8 [B8*16 rows][nblk*64 cols] bf16 (B8 = batch rounded up to 8), box (64, 128)
+  CUtensorMap mapA2;         // split mode: its lo half
   const bf16* dY;            // dY0 [B][16][16][Pp]
+  const bf16* dYlo;          // split mode: its lo half
   float* part;               // [nsplit][Q16][KA (n)][KA (k)] fp32
   int B, F, P, Pp, KA, nblk, Q16, nsplit;
 };
 
 // A8[(b,h)][2i+d] = o_i[b, 2h+d] in bf16, zero beyond 2F and for padded samples: the A tile of every 8-sample tile
-__global__ void k_build_a8(const float* __restrict__ rows, int B, int B8, int F, int KP, bf16* __restrict__ out) {
+__global__ void k_build_a8(const float* __restrict__ rows, int B, int B8, int F, int KP, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
   const int64_t total = (int64_t)B8 * 16 * (KP / 2);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(e % (KP / 2));
@@ -54,6 +64,7 @@ __global__ void k_build_a8(const float* __restrict__ rows, int B, int B8, int F,
     float2 o = make_float2(0.f, 0.f);
     if (i < F && b < B) o = *reinterpret_cast<const float2*>(rows + (b * F + i) * 32 + 2 * h);
     reinterpret_cast<uint32_t*>(out)[e] = pack2(o.x, o.y);
+    if (out_lo) reinterpret_cast<uint32_t*>(out_lo)[e] = pack2_lo(o.x, o.y);
   }
 }
 
@@ -72,12 +83,15 @@ __global__ void k_wfact_reduce(const float* __restrict__ part, const int* __rest
   }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_constant__ Wgrad0FactParams prm) {
+  constexpr int NP = SPLIT ? 2 : 1;                      // precision parts of an operand: hi (, lo)
+  constexpr int ABUF = NP * G0_DQ_BYTES, DBUF = NP * W0_DQC_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sAt = smem;                                   // 2 A tiles
-  uint8_t* sDq = sAt + 2 * G0_DQ_BYTES;                  // W0_ND block-diagonal dY buffers
-  W0Ctl* ctl = reinterpret_cast<W0Ctl*>(sDq + W0_ND * G0_DQ_BYTES);
+  uint8_t* sAt = smem;                                   // 2 A tiles (split: hi tile, lo tile)
+  uint8_t* sDq = sAt + 2 * ABUF;                         // W0_ND buffers of compact dY0 blocks (split: hi, lo)
+  W0Ctl* ctl = reinterpret_cast<W0Ctl*>(sDq + W0_ND * DBUF);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -91,7 +105,7 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
 
   if (warp == 1 && lane == 0) {
     for (int b = 0; b < 2; ++b) { mbar_init(&ctl->a_ready[b], 1); mbar_init(&ctl->a_free[b], 1); mbar_init(&ctl->grp_done[b], 4); }
-    for (int d = 0; d < W0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4); mbar_init(&ctl->dq_empty[d], 1); }
+    for (int d = 0; d < W0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4 * NP); mbar_init(&ctl->dq_empty[d], 1); }
     for (int e = 0; e < W0_NE; ++e) {
       mbar_init(&ctl->e_full[e], 1); mbar_init(&ctl->e_conv[e], 4); mbar_init(&ctl->e_empty[e], 1);
     }
@@ -99,8 +113,6 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
     fence_barrier_init();
   }
   if (warp == 3) tmem_alloc(&ctl->tmem_base, 512);
-  for (int e = threadIdx.x; e < W0_ND * G0_DQ_BYTES / 16; e += W0_THREADS) reinterpret_cast<uint4*>(sDq)[e] = make_uint4(0u, 0u, 0u, 0u);
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -109,6 +121,7 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA: A tiles
     prefetch_tmap(&prm.mapA);
+    if (SPLIT) prefetch_tmap(&prm.mapA2);
     uint32_t T = 0;
     for (int it = 0; it < my_units; ++it) {
       int t0, t1; unit_tiles((int)blockIdx.x + it * (int)gridDim.x, t0, t1);
@@ -116,18 +129,20 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
         const int ab = T & 1;
         mbar_wait(&ctl->a_free[ab], ((T >> 1) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&ctl->a_ready[ab], (uint32_t)(prm.nblk * A_STAGE_BYTES));
-          for (int blk = 0; blk < prm.nblk; ++blk)
-            tma_load_2d(sAt + ab * G0_DQ_BYTES + blk * A_STAGE_BYTES, &prm.mapA, &ctl->a_ready[ab], blk * 64, t * BM);
+          mbar_arrive_expect_tx(&ctl->a_ready[ab], (uint32_t)(NP * prm.nblk * A_STAGE_BYTES));
+          for (int blk = 0; blk < prm.nblk; ++blk) {
+            tma_load_2d(sAt + ab * ABUF + blk * A_STAGE_BYTES, &prm.mapA, &ctl->a_ready[ab], blk * 64, t * BM);
+            if (SPLIT) tma_load_2d(sAt + ab * ABUF + G0_DQ_BYTES + blk * A_STAGE_BYTES, &prm.mapA2, &ctl->a_ready[ab], blk * 64, t * BM);
+          }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ E MMAs: M = 128 (n), N = 128 (b,h), K = 128 (b',w)
+    // ------------------------------------------------------------------ E MMAs
     const uint32_t at_addr = smem_u32(sAt), dq_addr = smem_u32(sDq);
-    // The block-diagonal structure is exploited exactly: one M=128 x N=16 x K=16 MMA per sample (rows and
-    // columns b*16 .. b*16+15 of Dq, the 16 rows of the A tile that belong to sample b), no accumulation.
+    // One M=128 (n) x N=16 (h) x K=16 (w) MMA per sample: the sample's 16 x 16 block of dY0 and the 16 rows of the A
+    // tile that belong to it, no accumulation over samples (split mode: three MMAs into the same columns).
     const uint32_t idesc = umma_idesc_bf16(BM, 16, true, false);
     uint32_t T = 0, n = 0; int d = 0; uint32_t dph = 0;
     for (int it = 0; it < my_units; ++it) {
@@ -137,9 +152,11 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
         mbar_wait(&ctl->a_ready[ab], (T >> 1) & 1);
         tc_fence_after();
         // descriptors: base of the tile / buffer + a constant per sample (start-address field counts 16-byte units)
-        const uint64_t a_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
+        const uint64_t a_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * ABUF), A_STAGE_BYTES, 1024);
+        const uint64_t a_lo = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * ABUF + G0_DQ_BYTES), A_STAGE_BYTES, 1024);
         for (int j = 0; j < W0_QS; ++j) {
-          const uint64_t b_base = umma_desc_k_sw128(dq_addr + (uint32_t)(d * G0_DQ_BYTES));
+          const uint64_t b_base = umma_desc_k_sw128(dq_addr + (uint32_t)(d * DBUF));
+          const uint64_t b_lo = umma_desc_k_sw128(dq_addr + (uint32_t)(d * DBUF + W0_DQC_BYTES));
           mbar_wait(&ctl->dq_full[d], dph);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf, ++n) {   // an item is half a tile: 4 samples, 64 columns of E^T
@@ -151,8 +168,12 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
 #pragma unroll
               for (int sb = 0; sb < 4; ++sb) {
                 const int ks = hf * 4 + sb;         // sample of the tile
-                umma_bf16(et + (uint32_t)(sb * 16), a_base + (uint64_t)(ks * (2048 >> 4)),
-                          b_base + (uint64_t)((((ks >> 2) * A_STAGE_BYTES + ks * 2048) >> 4) + (ks & 3) * 2), idesc, false);
+                const uint64_t ao = (uint64_t)(ks * (2048 >> 4)), bo = (uint64_t)((((ks >> 2) * 2048) >> 4) + (ks & 3) * 2);
+                umma_bf16(et + (uint32_t)(sb * 16), a_base + ao, b_base + bo, idesc, false);
+                if (SPLIT) {
+                  umma_bf16(et + (uint32_t)(sb * 16), a_lo + ao, b_base + bo, idesc, true);
+                  umma_bf16(et + (uint32_t)(sb * 16), a_base + ao, b_lo + bo, idesc, true);
+                }
               }
               umma_commit(&ctl->e_full[e]);
               if (hf == 1) umma_commit(&ctl->dq_empty[d]);
@@ -174,7 +195,8 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++T) {
         const int ab = T & 1;
-        const uint64_t b_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * G0_DQ_BYTES), A_STAGE_BYTES, 1024);
+        const uint64_t b_base = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * ABUF), A_STAGE_BYTES, 1024);
+        const uint64_t b_lo = umma_desc_mn_sw128(at_addr + (uint32_t)(ab * ABUF + G0_DQ_BYTES), A_STAGE_BYTES, 1024);
         const bool acc0 = t != t0;
 #pragma unroll
         for (int j = 0; j < W0_QS; ++j) {
@@ -186,9 +208,15 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int sb = 0; sb < 4; ++sb)
-                umma_bf16_ts(tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE), et + (uint32_t)(sb * 8),
-                             b_base + (uint64_t)((hf * 4 + sb) * (2048 >> 4)), idesc, acc0 || hf != 0 || sb != 0);
+              for (int sb = 0; sb < 4; ++sb) {
+                const uint32_t dw = tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE);
+                const uint64_t bo = (uint64_t)((hf * 4 + sb) * (2048 >> 4));
+                umma_bf16_ts(dw, et + (uint32_t)(sb * 8), b_base + bo, idesc, acc0 || hf != 0 || sb != 0);
+                if (SPLIT) {   // E^T hi in columns 0..31, lo in 32..63
+                  umma_bf16_ts(dw, et + (uint32_t)(32 + sb * 8), b_base + bo, idesc, true);
+                  umma_bf16_ts(dw, et + (uint32_t)(sb * 8), b_lo + bo, idesc, true);
+                }
+              }
               umma_commit(&ctl->e_empty[e]);
               if (j == W0_QS - 1 && hf == 1) umma_commit(&ctl->a_free[ab]);
               if (j == W0_QS - 1 && hf == 1 && t == t1 - 1) umma_commit(&ctl->dw_full);
@@ -217,6 +245,23 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
           const uint32_t ea = tmem_base + lane_off + (uint32_t)(W0_E + e * W0_E_STRIDE);
           mbar_wait(&ctl->e_full[e], eph);
           tc_fence_after();
+          if constexpr (SPLIT) {
+            // all 64 columns are read first: hi words go to columns 0..31, lo words to 32..63
+            float v[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld16(ea + (uint32_t)(c * 16), v[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
+              tmem_st8(ea + (uint32_t)(c * 8), pk);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2_lo(v[c][2 * jj], v[c][2 * jj + 1]);
+              tmem_st8(ea + (uint32_t)(32 + c * 8), pk);
+            }
+          } else
           // two passes of 32 columns; pass p writes bf16 columns 16p.., whose fp32 content has been read
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
@@ -263,13 +308,16 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       if (lane == 0) mbar_arrive(&ctl->dw_empty);
     }
   } else {
-    // ------------------------------------------------------------------ builders: groups alternate tiles
+    // ------------------------------------------------------------------ builders: groups alternate tiles (split mode:
+    // every tile, group 0 the hi blocks, group 1 the lo blocks)
     const int grp = (warp - 12) >> 2;
     const int r = (warp & 3) * 32 + lane;
     const int bl = r >> 4, h = r & 15;
-    const uint32_t dq_off = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2);
-    const uint32_t dq_off2 = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2 + 1);
-    // T = index of a (unit, tile) pair in this CTA's walk; group g takes the pairs with T & 1 == g
+    const uint32_t dq_off = (uint32_t)((SPLIT ? grp * W0_DQC_BYTES : 0) + (bl >> 2) * 2048) + sw128_offset(h, (bl & 3) * 2);
+    const uint32_t dq_off2 = (uint32_t)((SPLIT ? grp * W0_DQC_BYTES : 0) + (bl >> 2) * 2048) + sw128_offset(h, (bl & 3) * 2 + 1);
+    const bf16* dYsrc = SPLIT && grp == 1 ? prm.dYlo : prm.dY;
+    constexpr uint32_t TSTEP = SPLIT ? 1 : 2;
+    // T = index of a (unit, tile) pair in this CTA's walk; group g takes the pairs with T & 1 == g (split mode: all)
     auto decode = [&](uint32_t T, int& t, int& q0) -> bool {
       uint32_t acc = 0;
       for (int it = 0; it < my_units; ++it) {
@@ -285,11 +333,11 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
     auto issue = [&](int t, int q0) {
       const int b = t * 8 + bl;
       const bool ok = b < prm.B;
-      const bf16* src = prm.dY + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + q0;
+      const bf16* src = dYsrc + (((int64_t)(ok ? b : 0) * 16 + h) * 16) * prm.Pp + q0;
 #pragma unroll
       for (int w = 0; w < 16; ++w) raw[w] = ok ? __ldg(reinterpret_cast<const uint2*>(src + (int64_t)w * prm.Pp)) : make_uint2(0u, 0u);
     };
-    uint32_t T = (uint32_t)grp;
+    uint32_t T = SPLIT ? 0u : (uint32_t)grp;
     int t, q0;
     bool have = decode(T, t, q0);
     if (have) issue(t, q0);
@@ -305,24 +353,24 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
       }
       // next tile of this group: loads in flight while this tile's blocks are placed
       int tn, qn;
-      const bool have_next = decode(T + 2, tn, qn);
+      const bool have_next = decode(T + TSTEP, tn, qn);
       if (have_next) issue(tn, qn);
       // ring order: the other group must have finished the previous tile's channels
-      if (T >= 1) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((T - 1) >> 1)) & 1));
+      if (!SPLIT && T >= 1) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((T - 1) >> 1)) & 1));
 #pragma unroll
       for (int j = 0; j < W0_QS; ++j) {
         const uint32_t m = T * W0_QS + j;
         const int d = m % W0_ND; const uint32_t dph = (m / W0_ND) & 1;
         mbar_wait(&ctl->dq_empty[d], dph ^ 1);
-        uint8_t* base = sDq + d * G0_DQ_BYTES;
+        uint8_t* base = sDq + d * DBUF;
         *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(cur[j][0], cur[j][1], cur[j][2], cur[j][3]);
         *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(cur[j][4], cur[j][5], cur[j][6], cur[j][7]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
       }
-      if (lane == 0) mbar_arrive(&ctl->grp_done[grp]);
-      T += 2; t = tn; q0 = qn; have = have_next;
+      if (!SPLIT && lane == 0) mbar_arrive(&ctl->grp_done[grp]);
+      T += TSTEP; t = tn; q0 = qn; have = have_next;
     }
   }
   tc_fence_before();

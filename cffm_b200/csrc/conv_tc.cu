@@ -954,6 +954,7 @@ struct TCState {
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
   float* wf_part = nullptr;      // [W0_SPLIT_MAX][Q16][KA][KA] partial sums of the factorised layer-0 weight gradient
   bf16* A8 = nullptr;            // [B8*16][nblk*64] bf16 rows a_{b,h} (A tiles of the factorised weight gradient)
+  bf16* A8lo = nullptr;          // split mode: their lo halves
   int KA = 0, nblk = 0, Q16 = 0;
   int fact_min_batch = 512;      // the factorised kernels have a fixed cost (they win from a few hundred samples on)
   TmaEncoder enc;
@@ -1019,8 +1020,8 @@ int tc_alloc(Model* m, bool train) {
     const char* mf = getenv("CFFM_FACT_MIN_FIELDS");
     if (mb) st->fact_min_batch = atoi(mb);
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
-    // (split mode: the forward kernel splits its intermediate Z into hi + lo as well; the factorised data and weight
-    // gradients round their intermediates to bf16 and are not used, layer 0's backward stays in the direct form)
+    // (split mode: the forward and weight-gradient kernels split their intermediates (Z, E^T) into hi + lo as well; the
+    // factorised data gradient rounds its intermediate to bf16 and is not used, layer 0's data gradient stays direct)
     // (gelu keeps layer 0 in the direct form: only the k_tc epilogues store the derivative it trains with)
     if (m->Ko == 32 && m->cfg.activation != CFFM_ACT_GELU && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) &&
         !(f0 && !strcmp(f0, "direct"))) {
@@ -1063,10 +1064,11 @@ int tc_alloc(Model* m, bool train) {
       TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));
     }
     const char* w0 = getenv("CFFM_WGRAD0");
-    if (st->Wf0 && !st->split && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
+    if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
     {
       TCTRY(tcmalloc(m, &st->wf_part, (int64_t)W0_SPLIT_MAX * st->Q16 * st->KA * st->KA));
       TCTRY(tcmalloc(m, &st->A8, ((B + 7) / 8 * 8) * 16 * st->nblk * 64));
+      if (st->split) TCTRY(tcmalloc(m, &st->A8lo, ((B + 7) / 8 * 8) * 16 * st->nblk * 64));
     }
   }
   return CFFM_OK;
@@ -1091,6 +1093,7 @@ void tc_free(Model* m) {
   if (st->df_bpart) dev_free(st->df_bpart);
   if (st->wf_part) dev_free(st->wf_part);
   if (st->A8) dev_free(st->A8);
+  if (st->A8lo) dev_free(st->A8lo);
   delete st;
   m->tcs = nullptr;
 }
@@ -1344,20 +1347,21 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       if (l == 0 && st->wf_part && B >= st->fact_min_batch) {
         Wgrad0FactParams p;
         const int B8 = (B + 7) / 8 * 8, KP = st->nblk * 64;
-        k_build_a8<<<148 * 4, 256, 0, s>>>(m->outer_rows, B, B8, m->F, KP, st->A8);
-        memset(&p.mapA, 0, sizeof(p.mapA));
+        k_build_a8<<<148 * 4, 256, 0, s>>>(m->outer_rows, B, B8, m->F, KP, st->A8, st->A8lo);
+        memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->A8, (int64_t)B8 * 16, KP, BM, 64));
-        p.dY = st->dY[0]; p.part = st->wf_part;
+        if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapA2, st->A8lo, (int64_t)B8 * 16, KP, BM, 64));
+        p.dY = st->dY[0]; p.dYlo = st->dYlo[0]; p.part = st->wf_part;
         p.B = B; p.F = m->F; p.P = P; p.Pp = Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
         p.nsplit = std::min(W0_SPLIT_MAX, (B + 7) / 8);
         static PerDeviceOnce attr_once;
         bool& attr_done = attr_once();
         if (!attr_done) {
-          CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_wgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, W0_SMEM));
+          CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_wgrad0_fact<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, w0_smem(SPLIT)));
           attr_done = true;
         }
         const int units = (st->Q16 / W0_QS) * p.nsplit;
-        k_wgrad0_fact<<<units < 148 ? units : 148, W0_THREADS, W0_SMEM, s>>>(p);
+        k_wgrad0_fact<SPLIT><<<units < 148 ? units : 148, W0_THREADS, w0_smem(SPLIT), s>>>(p);
         const int64_t tot = 4ll * P * P;
         int rb = (int)((tot + 255) / 256); if (rb > 148 * 8) rb = 148 * 8;
         k_wfact_reduce<<<rb, 256, 0, s>>>(st->wf_part, m->pair_i, m->pair_j, P, st->KA, st->Q16, p.nsplit, g + m->lay.conv_w[0]);
