@@ -12,43 +12,55 @@
 // so the 3 GB cube gradient never exists, the result needs no cross-lane reduction, and the tensor work is
 // 2 x (8 + 5) small MMAs per (tile, q): 3x fewer tensor cycles than the direct form (whose epilogue was the limit).
 //
-//   warp 0       TMA: the two filter slabs of q (Wf0T[q] for term 1, Wf0[q] for term 2)
+// Both terms read ONE filter slab Wf0[q] (rows n, k contiguous): term 2 as a K-major B operand, term 1 as an MN-major
+// one (K = n runs over the slab's rows) -- no transposed copy of the filters, half the slab traffic.
+// Split mode (bf16x3): dY0, the A tile and the slab come as hi + lo, every product is hi*hi + lo*hi + hi*lo into the
+// same fp32 accumulator (three MMAs), E is split chunk by chunk (16 columns: hi words | lo words) in its own TMEM columns.  The operands
+// double in shared memory: one Dq buffer and two slab stages instead of two and three.
+//
+//   warp 0       TMA: the filter slab of q (split mode: hi and lo)
 //   warp 1       issues the E MMAs (SS; A = Dq K-major / MN-major, B = the A tile as an MN-major operand)
 //   warp 2       issues the accumulating MMAs (TS: E as bf16 in TMEM)
 //   warp 3       TMEM allocation
 //   warps 4..7   convert E1 fp32 -> bf16 in place; at the end of a tile: D + pooling term -> g_rows
 //   warps 8..11  convert E2
 //   warps 12..19 two builder groups: dY0 (8 channels per load) -> diagonal blocks of Dq; group 0 also builds the A tile
+//                (the groups take alternate 8-channel sets; split mode: every set, group 0 the hi blocks, group 1 the lo)
 #pragma once
 
 constexpr int G0_THREADS = 640;
 // ring depths: E buffers in tensor memory, Dq buffers, filter-slab stages.  A slab stage is busy for (TMA latency + its
 // MMAs) ~ 1.5 + 0.55 us, so two stages fed the tensor pipe one channel per ~1 us; three stages (and two Dq buffers,
 // which only have to cover the builders' store + fence) fit the same shared memory.
-constexpr int G0_NE = 4, G0_ND = 2, G0_NW = 3;
+constexpr int G0_NE = 4, G0_ND_MAX = 2, G0_NW_MAX = 3;
+__host__ __device__ constexpr int g0_nd(bool split) { return split ? 1 : 2; }
+__host__ __device__ constexpr int g0_nw(bool split) { return split ? 2 : 3; }
 constexpr int G0_E = 0, G0_E_STRIDE = 80, G0_D = 320;
 constexpr int G0_DQ_BYTES = 2 * A_STAGE_BYTES;            // 128 rows x 128 columns bf16
-constexpr int G0_WSTAGE = 2 * F0_SLAB_BYTES;
 
 struct G0Ctl {
-  uint64_t w_full[G0_NW], w_empty[G0_NW], dq_full[G0_ND], dq_empty[G0_ND];
+  uint64_t w_full[G0_NW_MAX], w_empty[G0_NW_MAX], dq_full[G0_ND_MAX], dq_empty[G0_ND_MAX];
   uint64_t e_full[G0_NE], e_conv[G0_NE], e_empty[G0_NE];
   uint64_t a_ready, a_free, d_full, d_empty, grp_done[2];
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(G0Ctl) <= 256, "control block");
-constexpr int G0_SMEM = 1024 + 2 * A_STAGE_BYTES + G0_ND * G0_DQ_BYTES + G0_NW * G0_WSTAGE + 256;
-static_assert(G0_SMEM <= 227 * 1024, "factorised data gradient exceeds the shared memory of an SM");
+constexpr int g0_smem(bool split) {
+  return 1024 + (split ? 2 : 1) * (2 * A_STAGE_BYTES + g0_nd(split) * G0_DQ_BYTES + g0_nw(split) * F0_SLAB_BYTES) + 256;
+}
+static_assert(g0_smem(false) <= 227 * 1024 && g0_smem(true) <= 227 * 1024, "factorised data gradient exceeds the shared memory of an SM");
 
 struct Dgrad0FactParams {
-  CUtensorMap mapW, mapWT;   // Wf0 [q][n][k] and Wf0T [q][k][n], both viewed as [Q16*KA rows][nblk*64 cols], box (64, KA)
+  CUtensorMap mapW, mapW2;   // Wf0 [q][n][k] (split mode: and its lo half) viewed as [Q16*KA rows][nblk*64 cols], box (64, KA)
   const bf16* dY;            // dY0 [B][16][16][Pp]
+  const bf16* dYlo;          // split mode: its lo half
   const float* rows;         // outer rows [B][F][32]
   const float* gout;         // [B]
   const float* v_head;       // pooling weights of level 0: v[0..31]
   const float2* pterm;       // [B][F]: (sum_{j>f} S_j, sum_{i<f} T_i), S_j = sum_c o_j[c], T_i = sum_a v[a] o_i[a]
   float* g_rows;             // [B][F][32]
-  float* bpart;              // [tiles][4 warps][Q16]: column sums of dY0 per builder warp (bias gradient of layer 0)
+  float* bpart;              // [tiles][4 warps][Q16]: column sums of dY0 per builder warp (bias gradient of layer 0);
+                             // null in split mode (the column sums of hi + lo are taken by k_colsum_bf16)
   int B, F, P, Pp, KA, nblk, Q16;
 };
 
@@ -88,13 +100,18 @@ __global__ void k_pool_terms0(const float* __restrict__ rows, const float* __res
   if (lane + 32 < F) o[lane + 32] = make_float2(totS1 - iS1, totT0 + (iT1 - T1));
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_constant__ Dgrad0FactParams prm) {
+  constexpr int NP = SPLIT ? 2 : 1;                      // precision parts of an operand: hi (, lo)
+  constexpr int G0_ND = g0_nd(SPLIT), G0_NW = g0_nw(SPLIT);
+  constexpr int ABYTES = 2 * A_STAGE_BYTES;              // one part of the A tile
+  constexpr int DBUF = NP * G0_DQ_BYTES, WSTAGE = NP * F0_SLAB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sAt = smem;                                   // A tile [2 blocks][128 rows][128 B]
-  uint8_t* sDq = sAt + 2 * A_STAGE_BYTES;                // G0_ND buffers of [2 blocks][128 rows][128 B]
-  uint8_t* sW = sDq + G0_ND * G0_DQ_BYTES;               // G0_NW stages of {Wf0T slab, Wf0 slab}
-  G0Ctl* ctl = reinterpret_cast<G0Ctl*>(sW + G0_NW * G0_WSTAGE);
+  uint8_t* sAt = smem;                                   // A tile [2 blocks][128 rows][128 B] (split: hi tile, lo tile)
+  uint8_t* sDq = sAt + NP * ABYTES;                      // G0_ND buffers of [2 blocks][128 rows][128 B] (split: hi, lo)
+  uint8_t* sW = sDq + G0_ND * DBUF;                      // G0_NW stages of the Wf0 slab (split: hi, lo)
+  G0Ctl* ctl = reinterpret_cast<G0Ctl*>(sW + G0_NW * WSTAGE);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -104,10 +121,10 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
   const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t slab_bytes = (uint32_t)(nblk * KA * 128);
 
-  if (warp == 0 && lane == 0) { prefetch_tmap(&prm.mapW); prefetch_tmap(&prm.mapWT); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&prm.mapW); if (SPLIT) prefetch_tmap(&prm.mapW2); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G0_NW; ++s) { mbar_init(&ctl->w_full[s], 1); mbar_init(&ctl->w_empty[s], 1); }
-    for (int d = 0; d < G0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4); mbar_init(&ctl->dq_empty[d], 1); }
+    for (int d = 0; d < G0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4 * NP); mbar_init(&ctl->dq_empty[d], 1); }
     for (int e = 0; e < G0_NE; ++e) { mbar_init(&ctl->e_full[e], 1); mbar_init(&ctl->e_conv[e], 4); mbar_init(&ctl->e_empty[e], 1); }
     mbar_init(&ctl->a_ready, 4); mbar_init(&ctl->a_free, 1); mbar_init(&ctl->d_full, 1); mbar_init(&ctl->d_empty, 4);
     mbar_init(&ctl->grp_done[0], 4); mbar_init(&ctl->grp_done[1], 4);
@@ -115,7 +132,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
   }
   if (warp == 3) tmem_alloc(&ctl->tmem_base, 512);
   // the off-diagonal part of the Dq buffers is zero for ever
-  for (int e = threadIdx.x; e < G0_ND * G0_DQ_BYTES / 16; e += G0_THREADS) reinterpret_cast<uint4*>(sDq)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = threadIdx.x; e < G0_ND * DBUF / 16; e += G0_THREADS) reinterpret_cast<uint4*>(sDq)[e] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -130,10 +147,10 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         const int s = n % G0_NW; const uint32_t ph = (n / G0_NW) & 1;
         mbar_wait(&ctl->w_empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&ctl->w_full[s], 2 * slab_bytes);
+          mbar_arrive_expect_tx(&ctl->w_full[s], NP * slab_bytes);
           for (int blk = 0; blk < nblk; ++blk) {
-            tma_load_2d(sW + s * G0_WSTAGE + blk * KA * 128, &prm.mapWT, &ctl->w_full[s], blk * 64, q * KA);
-            tma_load_2d(sW + s * G0_WSTAGE + F0_SLAB_BYTES + blk * KA * 128, &prm.mapW, &ctl->w_full[s], blk * 64, q * KA);
+            tma_load_2d(sW + s * WSTAGE + blk * KA * 128, &prm.mapW, &ctl->w_full[s], blk * 64, q * KA);
+            if (SPLIT) tma_load_2d(sW + s * WSTAGE + F0_SLAB_BYTES + blk * KA * 128, &prm.mapW2, &ctl->w_full[s], blk * 64, q * KA);
           }
         }
         __syncwarp();
@@ -145,21 +162,25 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
     uint64_t bdesc[8];
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) bdesc[ks] = umma_desc_mn_sw128(at_addr + (uint32_t)(ks * 2048), A_STAGE_BYTES, 1024);
+    constexpr uint64_t B_LO = (uint64_t)(ABYTES >> 4), D_LO = (uint64_t)(G0_DQ_BYTES >> 4);   // lo parts, in descriptor units
     uint32_t n = 0; int d = 0; uint32_t dph = 0;
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&ctl->a_ready, (uint32_t)(t & 1));
       tc_fence_after();
       for (int q = 0; q < Q; ++q, ++n) {
         const int e1 = (n & 1) * 2; const uint32_t eph = (n >> 1) & 1;
-        const uint32_t dq = dq_addr + (uint32_t)(d * G0_DQ_BYTES);
+        const uint32_t dq = dq_addr + (uint32_t)(d * DBUF);
         mbar_wait(&ctl->dq_full[d], dph);
         mbar_wait(&ctl->e_empty[e1], eph ^ 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem_base + (uint32_t)(G0_E + e1 * G0_E_STRIDE),
-                      umma_desc_k_sw128(dq + (uint32_t)((ks >> 2) * A_STAGE_BYTES)) + (uint64_t)((ks & 3) * 2), bdesc[ks], idesc_k, ks != 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t et = tmem_base + (uint32_t)(G0_E + e1 * G0_E_STRIDE);
+            const uint64_t ad = umma_desc_k_sw128(dq + (uint32_t)((ks >> 2) * A_STAGE_BYTES)) + (uint64_t)((ks & 3) * 2);
+            umma_bf16(et, ad, bdesc[ks], idesc_k, ks != 0);
+            if (SPLIT) { umma_bf16(et, ad + D_LO, bdesc[ks], idesc_k, true); umma_bf16(et, ad, bdesc[ks] + B_LO, idesc_k, true); }
+          }
           umma_commit(&ctl->e_full[e1]);
         }
         __syncwarp();
@@ -167,9 +188,12 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_bf16(tmem_base + (uint32_t)(G0_E + (e1 + 1) * G0_E_STRIDE), umma_desc_mn_sw128(dq + (uint32_t)(ks * 2048), A_STAGE_BYTES, 1024),
-                      bdesc[ks], idesc_mn, ks != 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t et = tmem_base + (uint32_t)(G0_E + (e1 + 1) * G0_E_STRIDE);
+            const uint64_t ad = umma_desc_mn_sw128(dq + (uint32_t)(ks * 2048), A_STAGE_BYTES, 1024);
+            umma_bf16(et, ad, bdesc[ks], idesc_mn, ks != 0);
+            if (SPLIT) { umma_bf16(et, ad + D_LO, bdesc[ks], idesc_mn, true); umma_bf16(et, ad, bdesc[ks] + B_LO, idesc_mn, true); }
+          }
           umma_commit(&ctl->e_full[e1 + 1]);
           umma_commit(&ctl->dq_empty[d]);
           if (q == Q - 1) umma_commit(&ctl->a_free);
@@ -180,10 +204,15 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ accumulating MMAs (TS): M = 128, N = KA, K = KA
-    const uint32_t idesc = umma_idesc_bf16(BM, KA);
+    // term 2: B[N = c][K = k] = Wq[k, c] = slab row c, K-major; term 1: B[N = c][K = n] = Wq[c, n] = slab row n, column c:
+    // MN-major, a K step is 16 slab rows (2048 bytes), the two 64-column blocks are KA * 128 bytes apart
+    const uint32_t idesc = umma_idesc_bf16(BM, KA), idesc_t1 = umma_idesc_bf16(BM, KA, false, true);
     uint64_t wk[F0_KA_MAX / UMMA_K];
 #pragma unroll
     for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k) wk[k] = (uint64_t)((((k >> 2) * KA * 128) >> 4) + (k & 3) * 2);
+    constexpr uint64_t W_LO = (uint64_t)(F0_SLAB_BYTES >> 4);
+    constexpr uint32_t e_lo = 8;                           // split mode: a K step of E = 16 columns, hi words | lo words
+    constexpr uint32_t e_step = SPLIT ? 16 : 8;
     const uint32_t d_tmem = tmem_base + (uint32_t)G0_D;
     uint32_t n = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -191,14 +220,19 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
       for (int q = 0; q < Q; ++q, ++n) {
         const int s = n % G0_NW; const uint32_t wph = (n / G0_NW) & 1;
         const int e1 = (n & 1) * 2; const uint32_t eph = (n >> 1) & 1;
-        const uint64_t wT = umma_desc_k_sw128(smem_u32(sW + s * G0_WSTAGE)), wN = umma_desc_k_sw128(smem_u32(sW + s * G0_WSTAGE + F0_SLAB_BYTES));
+        const uint64_t wT = umma_desc_mn_sw128(smem_u32(sW + s * WSTAGE), (uint32_t)(KA * 128), 1024), wN = umma_desc_k_sw128(smem_u32(sW + s * WSTAGE));
         mbar_wait(&ctl->w_full[s], wph);
         mbar_wait(&ctl->e_conv[e1], eph);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-            if (k < ksteps) umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(G0_E + e1 * G0_E_STRIDE + k * 8), wT + wk[k], idesc, (q | k) != 0);
+            if (k < ksteps) {
+              const uint32_t ea = tmem_base + (uint32_t)(G0_E + e1 * G0_E_STRIDE) + (uint32_t)k * e_step;
+              const uint64_t wd = wT + (uint64_t)(k * (2048 >> 4));
+              umma_bf16_ts(d_tmem, ea, wd, idesc_t1, (q | k) != 0);
+              if (SPLIT) { umma_bf16_ts(d_tmem, ea + e_lo, wd, idesc_t1, true); umma_bf16_ts(d_tmem, ea, wd + W_LO, idesc_t1, true); }
+            }
           umma_commit(&ctl->e_empty[e1]);
         }
         __syncwarp();
@@ -207,7 +241,11 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < F0_KA_MAX / UMMA_K; ++k)
-            if (k < ksteps) umma_bf16_ts(d_tmem, tmem_base + (uint32_t)(G0_E + (e1 + 1) * G0_E_STRIDE + k * 8), wN + wk[k], idesc, true);
+            if (k < ksteps) {
+              const uint32_t ea = tmem_base + (uint32_t)(G0_E + (e1 + 1) * G0_E_STRIDE) + (uint32_t)k * e_step;
+              umma_bf16_ts(d_tmem, ea, wN + wk[k], idesc, true);
+              if (SPLIT) { umma_bf16_ts(d_tmem, ea + e_lo, wN + wk[k], idesc, true); umma_bf16_ts(d_tmem, ea, wN + wk[k] + W_LO, idesc, true); }
+            }
           umma_commit(&ctl->e_empty[e1 + 1]);
           umma_commit(&ctl->w_empty[s]);
           if (q == Q - 1) umma_commit(&ctl->d_full);
@@ -229,6 +267,29 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         const uint32_t ea = tmem_base + lane_off + (uint32_t)(G0_E + e * G0_E_STRIDE);
         mbar_wait(&ctl->e_full[e], eph);
         tc_fence_after();
+        if constexpr (SPLIT) {
+          // every 16-column chunk in place: its hi words -> the chunk's columns 0..7, its lo words -> 8..15 (a chunk is
+          // one K step of the accumulating MMAs; nothing has to wait in registers for other columns to be read)
+#pragma unroll
+          for (int pass = 0; pass < (F0_KA_MAX / 16 + 1) / 2; ++pass) {
+            float v[2][16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if ((2 * pass + c) * 16 < KA && 2 * pass + c < F0_KA_MAX / 16) tmem_ld16(ea + (uint32_t)((2 * pass + c) * 16), v[c]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if ((2 * pass + c) * 16 < KA && 2 * pass + c < F0_KA_MAX / 16) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack2(v[c][2 * j], v[c][2 * j + 1]);
+                tmem_st8(ea + (uint32_t)((2 * pass + c) * 16), pk);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack2_lo(v[c][2 * j], v[c][2 * j + 1]);
+                tmem_st8(ea + (uint32_t)((2 * pass + c) * 16 + 8), pk);
+              }
+          }
+        } else
         // two passes (48 + 32 columns) keep the register count inside the 640-thread budget; the bf16 words of
         // the first pass land in columns 0..23, which pass two has no need to read (it reads 48..79)
 #pragma unroll
@@ -288,10 +349,13 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
   } else {
     // ------------------------------------------------------------------ builders: dY0 -> diagonal blocks of Dq
     const int grp = (warp - 12) >> 2;                     // q groups of 8: group g takes those with (q >> 3) & 1 == g
+                                                          // (split mode: every group of 8; g = 0 the hi part, g = 1 the lo)
     const int r = (warp & 3) * 32 + lane;                 // tile row = (sample r >> 4, h = r & 15)
     const int bl = r >> 4, h = r & 15;
-    const uint32_t dq_off = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2);
-    const uint32_t dq_off2 = (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2 + 1);
+    const uint32_t part_off = SPLIT ? (uint32_t)(grp * G0_DQ_BYTES) : 0u;
+    const uint32_t dq_off = part_off + (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2);
+    const uint32_t dq_off2 = part_off + (uint32_t)((bl >> 2) * A_STAGE_BYTES) + sw128_offset(r, (bl & 3) * 2 + 1);
+    const bf16* dYsrc = SPLIT && grp == 1 ? prm.dYlo : prm.dY;
     uint32_t n = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
@@ -301,28 +365,31 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         if (t > 0) mbar_wait(&ctl->a_free, (uint32_t)((t - 1) & 1));
         const float* src = prm.rows + ((int64_t)(b < prm.B ? b : 0) * prm.F) * 32 + 2 * h;
         for (int c = 0; c < KA / 8; ++c) {
-          uint32_t wv[4];
+          uint32_t wv[4], wl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = 4 * c + e;
             float2 o = make_float2(0.f, 0.f);
             if (i < prm.F && b < prm.B) o = __ldg(reinterpret_cast<const float2*>(src + i * 32));
             wv[e] = pack2(o.x, o.y);
+            if (SPLIT) wl[e] = pack2_lo(o.x, o.y);
           }
           *reinterpret_cast<uint4*>(sAt + (c >> 3) * A_STAGE_BYTES + sw128_offset(r, c & 7)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          if (SPLIT)
+            *reinterpret_cast<uint4*>(sAt + ABYTES + (c >> 3) * A_STAGE_BYTES + sw128_offset(r, c & 7)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->a_ready);
       }
-      const bf16* src = prm.dY + (((int64_t)(b < prm.B ? b : 0) * 16 + h) * 16) * prm.Pp;
+      const bf16* src = dYsrc + (((int64_t)(b < prm.B ? b : 0) * 16 + h) * 16) * prm.Pp;
       for (int q0 = 0; q0 < Q; q0 += 8, n += 8) {
-        if (((q0 >> 3) & 1) != grp) continue;
+        if (!SPLIT && ((q0 >> 3) & 1) != grp) continue;
         uint4 dv[16];
 #pragma unroll
         for (int w = 0; w < 16; ++w)
           dv[w] = b < prm.B ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)w * prm.Pp + q0)) : make_uint4(0u, 0u, 0u, 0u);
-        {  // d b_0[q] = sum of dY0 over all positions: this warp's 32 rows x 16 w of the 8 channels (the data is here anyway)
+        if (!SPLIT) {  // d b_0[q] = sum of dY0 over all positions: this warp's 32 rows x 16 w of the 8 channels (the data is here anyway)
           float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int w = 0; w < 16; ++w) {
@@ -338,7 +405,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
         // The groups take the 8-channel groups alternately and must fill the Dq ring in channel order (a parity
         // wait cannot tell one ring revolution from the next): wait until the other group has finished the
         // preceding 8 channels.  n >> 3 = index of this 8-channel group over the whole kernel.
-        if (n >= 8) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((n >> 3) - 1) >> 1) & 1));
+        if (!SPLIT && n >= 8) mbar_wait(&ctl->grp_done[grp ^ 1], (uint32_t)((((n >> 3) - 1) >> 1) & 1));
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
           const uint32_t m = n + qq;
@@ -351,14 +418,14 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
             pk[w >> 1] = __byte_perm(a, c, (qq & 1) ? 0x7632 : 0x5410);
           }
           mbar_wait(&ctl->dq_empty[d], dph ^ 1);
-          uint8_t* base = sDq + d * G0_DQ_BYTES;
+          uint8_t* base = sDq + d * DBUF;
           *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
         }
-        if (lane == 0) mbar_arrive(&ctl->grp_done[grp]);
+        if (!SPLIT && lane == 0) mbar_arrive(&ctl->grp_done[grp]);
       }
     }
   }

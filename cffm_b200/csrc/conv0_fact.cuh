@@ -97,10 +97,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 
-// Wf0[q][n = 2j+dw][k = 2i+dh] = Wf0T[q][k][n] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
+// Wf0[q][n = 2j+dw][k = 2i+dh] = W0[dh][dw][p(i,j)][q]; entries with i >= j stay zero (set once at allocation)
 __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restrict__ pair_i, const int* __restrict__ pair_j, int P,
-                               int KA, int KP, bf16* __restrict__ out, bf16* __restrict__ outT, bf16* __restrict__ out_lo = nullptr,
-                               bf16* __restrict__ outT_lo = nullptr) {
+                               int KA, int KP, bf16* __restrict__ out, bf16* __restrict__ out_lo) {
   const int64_t total = 4ll * P * P;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(e % P);
@@ -110,12 +109,7 @@ __global__ void k_prep_w0_fact(const float* __restrict__ W0, const int* __restri
     const int k = 2 * pair_i[p] + dh, n = 2 * pair_j[p] + dw;
     const bf16 v = __float2bfloat16(W0[e]);
     out[((int64_t)q * KA + n) * KP + k] = v;
-    if (outT) outT[((int64_t)q * KA + k) * KP + n] = v;   // transposed slabs (data gradient, conv0_dfact.cuh)
-    if (out_lo) {
-      const bf16 vl = __float2bfloat16(W0[e] - __bfloat162float(v));
-      out_lo[((int64_t)q * KA + n) * KP + k] = vl;
-      if (outT_lo) outT_lo[((int64_t)q * KA + k) * KP + n] = vl;
-    }
+    if (out_lo) out_lo[((int64_t)q * KA + n) * KP + k] = __float2bfloat16(W0[e] - __bfloat162float(v));
   }
 }
 

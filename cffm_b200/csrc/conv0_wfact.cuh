@@ -12,7 +12,7 @@
 // regions of 16 rows (h) x 128 bytes, sample s of the tile in region s / 4 at byte columns 32 (s % 4) -- 4 KB per
 // channel instead of a 32 KB block-diagonal matrix.
 // Split mode (bf16x3): A8 and dY0 come as hi + lo; every product is hi*hi + lo*hi + hi*lo into the same fp32
-// accumulator (three MMAs), E^T is split into hi | lo bf16 halves of its own 64 TMEM columns, one builder group
+// accumulator (three MMAs), E^T is split sample by sample (16 columns: hi words | lo words) in place, one builder group
 // places the hi blocks and the other the lo blocks of every tile.
 // The accumulators of 4 channels stay in TMEM while the CTA walks its share of the batch, so a unit is
 // (4 channels) x (a third of the tiles); CTAs that run at the same time hold neighbouring channel sets and read
@@ -211,10 +211,11 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
               for (int sb = 0; sb < 4; ++sb) {
                 const uint32_t dw = tmem_base + (uint32_t)(W0_DW + j * W0_DW_STRIDE);
                 const uint64_t bo = (uint64_t)((hf * 4 + sb) * (2048 >> 4));
-                umma_bf16_ts(dw, et + (uint32_t)(sb * 8), b_base + bo, idesc, acc0 || hf != 0 || sb != 0);
-                if (SPLIT) {   // E^T hi in columns 0..31, lo in 32..63
-                  umma_bf16_ts(dw, et + (uint32_t)(32 + sb * 8), b_base + bo, idesc, true);
-                  umma_bf16_ts(dw, et + (uint32_t)(sb * 8), b_lo + bo, idesc, true);
+                const uint32_t ea = et + (uint32_t)(sb * (SPLIT ? 16 : 8));   // split: a sample's 16 columns = hi words | lo words
+                umma_bf16_ts(dw, ea, b_base + bo, idesc, acc0 || hf != 0 || sb != 0);
+                if (SPLIT) {
+                  umma_bf16_ts(dw, ea + 8, b_base + bo, idesc, true);
+                  umma_bf16_ts(dw, ea, b_lo + bo, idesc, true);
                 }
               }
               umma_commit(&ctl->e_empty[e]);
@@ -246,20 +247,23 @@ __global__ void __launch_bounds__(W0_THREADS, 1) k_wgrad0_fact(const __grid_cons
           mbar_wait(&ctl->e_full[e], eph);
           tc_fence_after();
           if constexpr (SPLIT) {
-            // all 64 columns are read first: hi words go to columns 0..31, lo words to 32..63
-            float v[4][16];
+            // sample by sample in place: the 16 columns of a sample -> its hi words (columns 0..7) | lo words (8..15)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld16(ea + (uint32_t)(c * 16), v[c]);
-            tmem_ld_wait();
+            for (int pass = 0; pass < 2; ++pass) {
+              float v[2][16];
+              tmem_ld16(ea + (uint32_t)(pass * 32), v[0]);
+              tmem_ld16(ea + (uint32_t)(pass * 32 + 16), v[1]);
+              tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t pk[8];
+              for (int c = 0; c < 2; ++c) {
+                uint32_t pk[8];
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
-              tmem_st8(ea + (uint32_t)(c * 8), pk);
+                for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2(v[c][2 * jj], v[c][2 * jj + 1]);
+                tmem_st8(ea + (uint32_t)(pass * 32 + c * 16), pk);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2_lo(v[c][2 * jj], v[c][2 * jj + 1]);
-              tmem_st8(ea + (uint32_t)(32 + c * 8), pk);
+                for (int jj = 0; jj < 8; ++jj) pk[jj] = pack2_lo(v[c][2 * jj], v[c][2 * jj + 1]);
+                tmem_st8(ea + (uint32_t)(pass * 32 + c * 16 + 8), pk);
+              }
             }
           } else
           // two passes of 32 columns; pass p writes bf16 columns 16p.., whose fp32 content has been read

@@ -949,7 +949,7 @@ struct TCState {
   bf16* Wf0 = nullptr;           // layer-0 filters of the factorised forward: [Q16][KA][nblk*64] (conv0_fact.cuh)
   bf16* Wf0lo = nullptr;         // split mode: their lo halves
   bf16* X1i = nullptr;           // split mode: X_1 as the factorised forward writes it (hi / lo interleaved per 8 channels)
-  bf16* Wf0T = nullptr;          // transposed slabs [Q16][KA][nblk*64] for the factorised data gradient
+  bool dfact = false;            // the layer-0 data gradient runs in factorised form (conv0_dfact.cuh)
   float* df_bpart = nullptr;     // [tiles][4][Q16] column sums of dY0 collected by the factorised data gradient
   float2* pterm0 = nullptr;      // [B][F] pooling terms of the layer-0 data gradient
   float* wf_part = nullptr;      // [W0_SPLIT_MAX][Q16][KA][KA] partial sums of the factorised layer-0 weight gradient
@@ -1020,8 +1020,7 @@ int tc_alloc(Model* m, bool train) {
     const char* mf = getenv("CFFM_FACT_MIN_FIELDS");
     if (mb) st->fact_min_batch = atoi(mb);
     // factorised layer-0 kernels: worthwhile when the direct form is big (P = F(F-1)/2 channels) and the batch is not tiny
-    // (split mode: the forward and weight-gradient kernels split their intermediates (Z, E^T) into hi + lo as well; the
-    // factorised data gradient rounds its intermediate to bf16 and is not used, layer 0's data gradient stays direct)
+    // (split mode: the kernels split their intermediates (Z, E^T, E) into hi + lo as well)
     // (gelu keeps layer 0 in the direct form: only the k_tc epilogues store the derivative it trains with)
     if (m->Ko == 32 && m->cfg.activation != CFFM_ACT_GELU && 2 * m->F <= F0_KA_MAX && m->F >= (mf ? atoi(mf) : 16) &&
         !(f0 && !strcmp(f0, "direct"))) {
@@ -1056,12 +1055,10 @@ int tc_alloc(Model* m, bool train) {
     TCTRY(tcmalloc(m, &st->wg_partial, st->wg_partial_floats));
     TCTRY(tcmalloc(m, &st->bg_partial, (int64_t)kMaxConv * 2 * 148 * (int64_t)m->P));
     const char* d0 = getenv("CFFM_DGRAD0");
-    if (st->Wf0 && !st->split && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
-      const int64_t n = (int64_t)st->Q16 * st->KA * st->nblk * 64;
-      TCTRY(tcmalloc(m, &st->Wf0T, n));
-      CFFM_CUDA_OK(m, cudaMemset(st->Wf0T, 0, sizeof(bf16) * (size_t)n));
+    if (st->Wf0 && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
+      st->dfact = true;
       TCTRY(tcmalloc(m, &st->pterm0, B * m->F));
-      TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));
+      if (!st->split) TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));   // (split: k_colsum_bf16 sums hi + lo)
     }
     const char* w0 = getenv("CFFM_WGRAD0");
     if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
@@ -1088,7 +1085,6 @@ void tc_free(Model* m) {
   if (st->Wf0) dev_free(st->Wf0);
   if (st->Wf0lo) dev_free(st->Wf0lo);
   if (st->X1i) dev_free(st->X1i);
-  if (st->Wf0T) dev_free(st->Wf0T);
   if (st->pterm0) dev_free(st->pterm0);
   if (st->df_bpart) dev_free(st->df_bpart);
   if (st->wf_part) dev_free(st->wf_part);
@@ -1181,26 +1177,29 @@ static int fwd0_fact_launch(Model* m, TCState* st, int B, int sp_off, cudaStream
   return CFFM_OK;
 }
 
+template <bool SPLIT>
 static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   Dgrad0FactParams p;
-  memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapWT, 0, sizeof(p.mapWT));
+  memset(&p.mapW, 0, sizeof(p.mapW)); memset(&p.mapW2, 0, sizeof(p.mapW2));
   TC_MAP_OK(m, mat_map(st, &p.mapW, st->Wf0, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
-  TC_MAP_OK(m, mat_map(st, &p.mapWT, st->Wf0T, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
-  p.dY = st->dY[0]; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pterm = st->pterm0; p.g_rows = m->g_outer_rows;
+  if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapW2, st->Wf0lo, (int64_t)st->Q16 * st->KA, st->nblk * 64, st->KA, 64));
+  p.dY = st->dY[0]; p.dYlo = st->dYlo[0]; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pterm = st->pterm0; p.g_rows = m->g_outer_rows;
   p.bpart = st->df_bpart;
   p.B = B; p.F = m->F; p.P = m->P; p.Pp = st->Pp; p.KA = st->KA; p.nblk = st->nblk; p.Q16 = st->Q16;
   static PerDeviceOnce attr_once;
   bool& attr_done = attr_once();
   if (!attr_done) {
-    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_dgrad0_fact, cudaFuncAttributeMaxDynamicSharedMemorySize, G0_SMEM));
+    CFFM_CUDA_OK(m, cudaFuncSetAttribute(k_dgrad0_fact<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g0_smem(SPLIT)));
     attr_done = true;
   }
   k_pool_terms0<<<(B + 7) / 8, 256, 0, s>>>(m->outer_rows, m->v_head, B, m->F, st->pterm0);
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
-  k_dgrad0_fact<<<grid, G0_THREADS, G0_SMEM, s>>>(p);
-  // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
-  k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * 4, st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
-  m->launches += 3;
+  k_dgrad0_fact<SPLIT><<<grid, G0_THREADS, g0_smem(SPLIT), s>>>(p);
+  m->launches += 2;
+  if (!SPLIT) {  // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
+    k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * 4, st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
+    m->launches++;
+  }
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
 }
@@ -1209,7 +1208,7 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   CFFM_PROF(m, "prep_weights_bf16", s);
   // layer 0: the direct kernels' bf16 copies are not needed when every layer-0 kernel of this call is the factorised one
-  const bool fact0 = st->Wf0 && B >= st->fact_min_batch && (!st->dY[0] || (st->Wf0T && st->wf_part));
+  const bool fact0 = st->Wf0 && B >= st->fact_min_batch && (!st->dY[0] || (st->dfact && st->wf_part));
   PrepLayers pa;
   memset(&pa, 0, sizeof(pa));
   int nl = 0;
@@ -1224,8 +1223,8 @@ int tc_prep_weights(Model* m, int B, cudaStream_t s) {
     m->launches++;
   }
   if (st->Wf0 && B >= st->fact_min_batch) {
-    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0, st->Wf0T,
-                                           st->Wf0lo, nullptr);
+    k_prep_w0_fact<<<148 * 8, 256, 0, s>>>(m->dense_w + m->lay.conv_w[0], m->pair_i, m->pair_j, m->P, st->KA, st->nblk * 64, st->Wf0,
+                                           st->Wf0lo);
     m->launches++;
   }
   CFFM_CUDA_OK(m, cudaGetLastError());
@@ -1316,7 +1315,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
   for (int l = m->n_live - 1; l >= 0; --l) {
     const Geom gm = make_geom(m, st, B, l);
     const int64_t rows = gm.M;
-    if (!colsum_late && !(l == 0 && st->Wf0T && B >= st->fact_min_batch)) {  // (layer 0, factorised: collected by k_dgrad0_fact)
+    if (!colsum_late && !(l == 0 && st->df_bpart && B >= st->fact_min_batch)) {  // (layer 0, factorised: collected by k_dgrad0_fact)
       CFFM_PROF(m, "colsum", s);
       const int C = (int)std::min<int64_t>(2 * 148, std::max<int64_t>(1, (rows + 63) / 64));
       const int CG = Pp / 8;
@@ -1401,8 +1400,8 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       const std::string tag = "conv_dgrad_l" + std::to_string(l);
       CFFM_PROF(m, tag.c_str(), s);
       Geom gd = gm; gd.tiles_n = 4 * Pp / gm.BN;
-      if (l == 0 && st->Wf0T && B >= st->fact_min_batch) {
-        TCTRY(dgrad0_fact_launch(m, st, B, s));
+      if (l == 0 && st->dfact && B >= st->fact_min_batch) {
+        TCTRY(dgrad0_fact_launch<SPLIT>(m, st, B, s));
       } else if (l == 0) {
         Conv0DgradTC p;
         p.g = gd; p.rows = m->outer_rows; p.gout = m->gout; p.v_head = m->v_head; p.pair_i = m->pair_i; p.pair_j = m->pair_j;
@@ -1438,7 +1437,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
     a.Pp = Pp; a.n = P; a.partial = st->bg_partial; a.partial_stride = (int64_t)2 * 148 * P;
     int maxC = 1, nl = 0;
     for (int l = 0; l < m->n_live; ++l) {
-      if (l == 0 && st->Wf0T && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
+      if (l == 0 && st->df_bpart && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
       const int64_t rows = (int64_t)B * (K >> (l + 1)) * (K >> (l + 1));
       a.X[nl] = st->dY[l]; a.Xlo[nl] = st->dYlo[l]; a.rows[nl] = rows;
       a.C[nl] = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));   // few chunks: the second stage walks them one by one
