@@ -27,11 +27,12 @@
 //   warps 12..19 two builder groups: dY0 (8 channels per load) -> diagonal blocks of Dq; group 0 also builds the A tile
 //                (the groups take alternate 8-channel sets; split mode: every set, group 0 the hi blocks, group 1 the lo)
 // Measured (B = 8192, F = 39): 4.3 ms in bf16; 20 ms in split mode against 12 ms of MMA work (E MMAs are bound by
-// their shared-memory operands, ~68 clk each).  Timing experiments with parts of the split kernel switched off put
-// 7 ms on the builders' global loads: both groups need the same channel set, so their load latency is not covered by
-// the other group as in bf16 mode, and neither registers (16 x 16 B per thread in flight) nor shared memory (209 of
-// 227 KB) leave room for a prefetch stage.  Alternating 4-channel sets with 8-byte loads was slower (26 ms), an L2
-// prefetch of the next set changed nothing.
+// their shared-memory operands, ~68 clk each; tensor pipe 48 % active).  With one Dq buffer the chain
+// E MMAs done -> builders store + fence -> E MMAs of the next channel is serial, and shared memory (209 of 227 KB) has
+// no room for a second one.  Tried without gain: alternating 4-channel sets with 8-byte loads (26 ms), an L2 prefetch
+// of the next set, the next set prefetched into registers (setmaxnreg 40 / 56 / 160 for MMA / converter / builder
+// warps: 21 ms).  Switching the builders' loads off looked 7 ms faster, but that run multiplied zeros (the step runs
+// under the power cap, 1.63 of 1.97 GHz) -- the loads are not what the kernel waits for.
 #pragma once
 
 constexpr int G0_THREADS = 640;
