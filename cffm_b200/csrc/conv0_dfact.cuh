@@ -67,7 +67,7 @@ struct Dgrad0FactParams {
   const float2* pterm;       // [B][F]: (sum_{j>f} S_j, sum_{i<f} T_i), S_j = sum_c o_j[c], T_i = sum_a v[a] o_i[a]
   float* g_rows;             // [B][F][32]
   float* bpart;              // [tiles][4 warps][Q16]: column sums of dY0 per builder warp (bias gradient of layer 0);
-                             // null in split mode (the column sums of hi + lo are taken by k_colsum_bf16)
+                             // split mode: [tiles][2 parts][4 warps][Q16], the sums of the hi and of the lo tensor
   int B, F, P, Pp, KA, nblk, Q16;
 };
 
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
 #pragma unroll
         for (int w = 0; w < 16; ++w)
           dv[w] = b < prm.B ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)w * prm.Pp + q0)) : make_uint4(0u, 0u, 0u, 0u);
-        if (!SPLIT) {  // d b_0[q] = sum of dY0 over all positions: this warp's 32 rows x 16 w of the 8 channels (the data is here anyway)
+        {  // d b_0[q] = sum of dY0 over all positions: this warp's 32 rows x 16 w of the 8 channels (the data is here anyway)
           float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int w = 0; w < 16; ++w) {
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
           float mine = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float v = warp_sum(cs[j]); if (lane == j) mine = v; }
-          if (lane < 8) prm.bpart[((int64_t)tile * 4 + (warp & 3)) * Q + q0 + lane] = mine;
+          if (lane < 8) prm.bpart[(((int64_t)tile * (SPLIT ? 2 : 1) + (SPLIT ? grp : 0)) * 4 + (warp & 3)) * Q + q0 + lane] = mine;
         }
         // The groups take the 8-channel groups alternately and must fill the Dq ring in channel order (a parity
         // wait cannot tell one ring revolution from the next): wait until the other group has finished the

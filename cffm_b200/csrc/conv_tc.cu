@@ -1058,7 +1058,7 @@ int tc_alloc(Model* m, bool train) {
     if (st->Wf0 && !(d0 && !strcmp(d0, "direct"))) {   // factorised layer-0 data gradient
       st->dfact = true;
       TCTRY(tcmalloc(m, &st->pterm0, B * m->F));
-      if (!st->split) TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * 4 * (int64_t)st->Q16));   // (split: k_colsum_bf16 sums hi + lo)
+      TCTRY(tcmalloc(m, &st->df_bpart, ((B + 7) / 8) * (st->split ? 8 : 4) * (int64_t)st->Q16));
     }
     const char* w0 = getenv("CFFM_WGRAD0");
     if (st->Wf0 && !(w0 && !strcmp(w0, "direct")))     // factorised layer-0 weight gradient
@@ -1195,11 +1195,9 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   k_pool_terms0<<<(B + 7) / 8, 256, 0, s>>>(m->outer_rows, m->v_head, B, m->F, st->pterm0);
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
   k_dgrad0_fact<SPLIT><<<grid, G0_THREADS, g0_smem(SPLIT), s>>>(p);
-  m->launches += 2;
-  if (!SPLIT) {  // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
-    k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * 4, st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
-    m->launches++;
-  }
+  // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
+  k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * (SPLIT ? 8 : 4), st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
+  m->launches += 3;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
 }

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 artefacts on one GPU: smoke, whole GPU suite, both bench arms, ncu launch list of the bench command,
-# ncu --set full of the gather / update kernels
+# ncu --set full of the split-mode layer-0 kernels
+cd /root/repo
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/z_gpu.txt 2>&1
 timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/z_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/z_smoke.log
@@ -11,6 +12,6 @@ CMD="python bench.py --steps 2 --warmup 3 --modes none --workloads none --no-cpu
 $CMD > gpurun_out/z_plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/z_launches_bench.csv $CMD > gpurun_out/z_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-python scratch/prof_step.py 8192 bf16 > gpurun_out/z_plain_step.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_gather_rows|k_seg_sums_chunks|k_seg_sums_fixup|k_apply_rows|k_inner_linear_fwd|k_inner_dense_grad" -s 6 -c 6 -o gpurun_out/z_update python scratch/prof_step.py 8192 bf16 > gpurun_out/z_ncu_update.log 2>&1
-echo "ncu update rc=$?"; ls -la gpurun_out/z_*
+python scratch/prof_step.py 8192 bf16x3 > gpurun_out/z_plain_step.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_fwd0_fact|k_deinterleave_x1|k_wgrad0_fact|k_dgrad0_fact" -s 4 -c 4 -o gpurun_out/z_layer0_split python scratch/prof_step.py 8192 bf16x3 > gpurun_out/z_ncu_layer0.log 2>&1
+echo "ncu layer0 rc=$?"; ls -la gpurun_out/z_*
