@@ -188,7 +188,7 @@ def executed_flops(spec, tag, B, precision):
     """FLOPs the kernel really issues when that differs from the algorithmic (direct-form) figure.
     bf16: the layer-0 kernels run the convolution over the rank-one cube in factorised form:
     per 8-sample tile and channel two (forward) or four (data gradient, weight gradient: two) small MMAs.
-    bf16x3: every contraction is three MMAs (hi*hi + lo*hi + hi*lo), direct form."""
+    bf16x3: every contraction is three MMAs (hi*hi + lo*hi + hi*lo); layer 0 factorised as in bf16, layers >= 1 direct."""
     if not tag.startswith("conv_"):
         return None
     F, P = spec["F"], spec["F"] * (spec["F"] - 1) // 2
@@ -208,7 +208,7 @@ def executed_flops(spec, tag, B, precision):
 
 
 FACT_WGRAD = True    # the layer-0 weight gradient runs in factorised form as well (conv0_wfact.cuh)
-SPLIT_FACT = ("conv_fwd_l0", "conv_wgrad_l0")   # layer-0 kernels that run in factorised form in split (bf16x3) mode
+SPLIT_FACT = ("conv_fwd_l0", "conv_wgrad_l0", "conv_dgrad_l0")   # layer-0 kernels that run in factorised form in split (bf16x3) mode
 
 
 def ncu_traffic(spec, tag, B, precision):
@@ -245,7 +245,7 @@ def roofline_of(spec, kernel_table, B, world, precision):
         return {"kernel": top, "bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(ach / peak, 5), "traffic": traffic, "share_of_step": kernel_table[top]["share"],
                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)",
-                "flops_counted": "executed by the tensor cores (factorised layer 0 in bf16; three MMAs per product in bf16x3)",
+                "flops_counted": "executed by the tensor cores (layer 0 in factorised form; three MMAs per product in bf16x3)",
                 "executed_flops_per_launch": ex, "algorithmic_flops_per_launch": amount,
                 "algorithmic_achieved": round(algo, 3), "algorithmic_frac": round(algo / peak, 5)}
     ach = (amount / (avg_ms / 1e3) / 1e9) if amount else 0.0

@@ -47,13 +47,14 @@ constexpr int G0_DQ_BYTES = 2 * A_STAGE_BYTES;            // 128 rows x 128 colu
 
 struct G0Ctl {
   uint64_t w_full[G0_NW_MAX], w_empty[G0_NW_MAX], dq_full[G0_ND_MAX], dq_empty[G0_ND_MAX];
+  uint64_t dqw_full[4], dqw_empty[4];   // split mode: the one Dq buffer is handed over per builder warp (two samples)
   uint64_t e_full[G0_NE], e_conv[G0_NE], e_empty[G0_NE];
   uint64_t a_ready, a_free, d_full, d_empty, grp_done[2];
   uint32_t tmem_base, pad;
 };
-static_assert(sizeof(G0Ctl) <= 256, "control block");
+static_assert(sizeof(G0Ctl) <= 512, "control block");
 constexpr int g0_smem(bool split) {
-  return 1024 + (split ? 2 : 1) * (2 * A_STAGE_BYTES + g0_nd(split) * G0_DQ_BYTES + g0_nw(split) * F0_SLAB_BYTES) + 256;
+  return 1024 + (split ? 2 : 1) * (2 * A_STAGE_BYTES + g0_nd(split) * G0_DQ_BYTES + g0_nw(split) * F0_SLAB_BYTES) + 512;
 }
 static_assert(g0_smem(false) <= 227 * 1024 && g0_smem(true) <= 227 * 1024, "factorised data gradient exceeds the shared memory of an SM");
 
@@ -71,13 +72,22 @@ struct Dgrad0FactParams {
   int B, F, P, Pp, KA, nblk, Q16;
 };
 
-// d b_0[q] = sum over tiles and builder warps (fixed order) of the column sums collected by k_dgrad0_fact
-__global__ void k_dfact_bias_reduce(const float* __restrict__ bpart, int rows, int Q16, int P, float* __restrict__ out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= P) return;
+// d b_0[q] = sum over tiles and builder warps (fixed order) of the column sums collected by k_dgrad0_fact.
+// Block = 32 channels x 32 row slices (slice s takes rows s, s + 32, ...), the slices meet in shared memory in slice order.
+__global__ void __launch_bounds__(1024) k_dfact_bias_reduce(const float* __restrict__ bpart, int rows, int Q16, int P, float* __restrict__ out) {
+  __shared__ float part[32][33];
+  const int q = blockIdx.x * 32 + threadIdx.x, sl = threadIdx.y;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += bpart[(int64_t)r * Q16 + q];
-  out[q] = s;
+  if (q < P)
+    for (int r = sl; r < rows; r += 32) s += bpart[(int64_t)r * Q16 + q];
+  part[sl][threadIdx.x] = s;
+  __syncthreads();
+  if (sl == 0 && q < P) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
+    out[q] = t;
+  }
 }
 
 // pooling term of the layer-0 data gradient, per sample and field (see Dgrad0FactParams::pterm)
@@ -132,6 +142,7 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G0_NW; ++s) { mbar_init(&ctl->w_full[s], 1); mbar_init(&ctl->w_empty[s], 1); }
     for (int d = 0; d < G0_ND; ++d) { mbar_init(&ctl->dq_full[d], 4 * NP); mbar_init(&ctl->dq_empty[d], 1); }
+    for (int w = 0; w < 4; ++w) { mbar_init(&ctl->dqw_full[w], 2); mbar_init(&ctl->dqw_empty[w], 1); }
     for (int e = 0; e < G0_NE; ++e) { mbar_init(&ctl->e_full[e], 1); mbar_init(&ctl->e_conv[e], 4); mbar_init(&ctl->e_empty[e], 1); }
     mbar_init(&ctl->a_ready, 4); mbar_init(&ctl->a_free, 1); mbar_init(&ctl->d_full, 1); mbar_init(&ctl->d_empty, 4);
     mbar_init(&ctl->grp_done[0], 4); mbar_init(&ctl->grp_done[1], 4);
@@ -177,6 +188,41 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
       for (int q = 0; q < Q; ++q, ++n) {
         const int e1 = (n & 1) * 2; const uint32_t eph = (n >> 1) & 1;
         const uint32_t dq = dq_addr + (uint32_t)(d * DBUF);
+        if constexpr (SPLIT) {
+          // One Dq buffer: K step ks of both terms reads only what builder warp ks / 2 wrote (the rows and columns of
+          // samples 2w, 2w + 1; everything else in those columns and rows is zero for ever), so the buffer changes hands
+          // warp by warp -- the builders rewrite the first samples of the next channel while the MMAs of the last
+          // samples of this one run, instead of after all 48.
+          mbar_wait(&ctl->e_empty[e1], eph ^ 1);
+          mbar_wait(&ctl->e_empty[e1 + 1], eph ^ 1);
+          const uint32_t et1 = tmem_base + (uint32_t)(G0_E + e1 * G0_E_STRIDE), et2 = et1 + (uint32_t)G0_E_STRIDE;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            mbar_wait(&ctl->dqw_full[w], n & 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 2 * w; ks < 2 * w + 2; ++ks) {
+                const uint64_t ak = umma_desc_k_sw128(dq + (uint32_t)((ks >> 2) * A_STAGE_BYTES)) + (uint64_t)((ks & 3) * 2);
+                const uint64_t am = umma_desc_mn_sw128(dq + (uint32_t)(ks * 2048), A_STAGE_BYTES, 1024);
+                umma_bf16(et1, ak, bdesc[ks], idesc_k, ks != 0);
+                umma_bf16(et1, ak + D_LO, bdesc[ks], idesc_k, true);
+                umma_bf16(et1, ak, bdesc[ks] + B_LO, idesc_k, true);
+                umma_bf16(et2, am, bdesc[ks], idesc_mn, ks != 0);
+                umma_bf16(et2, am + D_LO, bdesc[ks], idesc_mn, true);
+                umma_bf16(et2, am, bdesc[ks] + B_LO, idesc_mn, true);
+              }
+              umma_commit(&ctl->dqw_empty[w]);
+              if (w == 3) {
+                umma_commit(&ctl->e_full[e1]);
+                umma_commit(&ctl->e_full[e1 + 1]);
+                if (q == Q - 1) umma_commit(&ctl->a_free);
+              }
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         mbar_wait(&ctl->dq_full[d], dph);
         mbar_wait(&ctl->e_empty[e1], eph ^ 1);
         tc_fence_after();
@@ -424,13 +470,13 @@ __global__ void __launch_bounds__(G0_THREADS, 1) k_dgrad0_fact(const __grid_cons
             const uint32_t c = (qq >> 1) == 0 ? dv[w + 1].x : (qq >> 1) == 1 ? dv[w + 1].y : (qq >> 1) == 2 ? dv[w + 1].z : dv[w + 1].w;
             pk[w >> 1] = __byte_perm(a, c, (qq & 1) ? 0x7632 : 0x5410);
           }
-          mbar_wait(&ctl->dq_empty[d], dph ^ 1);
+          mbar_wait(SPLIT ? &ctl->dqw_empty[warp & 3] : &ctl->dq_empty[d], dph ^ 1);
           uint8_t* base = sDq + d * DBUF;
           *reinterpret_cast<uint4*>(base + dq_off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(base + dq_off2) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->dq_full[d]);
+          if (lane == 0) mbar_arrive(SPLIT ? &ctl->dqw_full[warp & 3] : &ctl->dq_full[d]);
         }
         if (!SPLIT && lane == 0) mbar_arrive(&ctl->grp_done[grp]);
       }

@@ -1196,7 +1196,7 @@ static int dgrad0_fact_launch(Model* m, TCState* st, int B, cudaStream_t s) {
   int grid = (B + 7) / 8; if (grid > 148) grid = 148;
   k_dgrad0_fact<SPLIT><<<grid, G0_THREADS, g0_smem(SPLIT), s>>>(p);
   // bias gradient of layer 0 from the column sums the builders collected (replaces the colsum pass over dY0)
-  k_dfact_bias_reduce<<<ceil_div(m->P, 128), 128, 0, s>>>(st->df_bpart, ((B + 7) / 8) * (SPLIT ? 8 : 4), st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
+  k_dfact_bias_reduce<<<ceil_div(m->P, 32), dim3(32, 32), 0, s>>>(st->df_bpart, ((B + 7) / 8) * (SPLIT ? 8 : 4), st->Q16, m->P, m->dense_g + m->lay.conv_b[0]);
   m->launches += 3;
   CFFM_CUDA_OK(m, cudaGetLastError());
   return CFFM_OK;
