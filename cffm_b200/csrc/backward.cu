@@ -573,6 +573,46 @@ int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, in
   if (m->world > 1) { int r = comm_allreduce_f32(m, m->scalars, 1, s); if (r != CFFM_OK) return r; }
   launch_loss_finish(m, B, s);
 
+  // ---- inner path + linear term (side stream: independent of the conv stack until the partial sums are folded) ----
+  const cudaStream_t side = side_fork(m, s);
+  {
+    InnerLinBwdArgs a;
+    a.ids = ids; a.B = B; a.F = F; a.P = P; a.K = m->cfg.inner_conv ? m->Ki : 4; a.lgK = ilog2(a.K);
+    a.n_small = m->n_small; a.inner_conv = m->cfg.inner_conv; a.linear_att = m->cfg.linear_att;
+    a.tab = tv.inner; a.fbias = tv.fbias; a.cw = w + L.iconv_w; a.cb = w + L.iconv_b; a.Wd = w + L.din_k;
+    a.attW = w + L.att_W; a.attb = w + L.att_b; a.w3 = w + L.d3_k;
+    a.pair_i = m->pair_i; a.pair_j = m->pair_j; a.tau = m->cfg.lamda_att; a.gout = m->gout;
+    a.g_inner_rows = m->g_inner_rows; a.g_bias_rows = m->g_bias_rows; a.rowbuf = m->rowbuf;
+    int wpb = 8;
+    while (wpb > 1 && inner_bwd_smem(F, P, a.K, wpb) > 96 * 1024) wpb >>= 1;
+    { CFFM_PROF(m, "inner_linear_bwd", side);
+    CFFM_DISPATCH_ACT(act, k_inner_linear_bwd<ACT><<<ceil_div(B, wpb), wpb * 32, inner_bwd_smem(F, P, a.K, wpb), side>>>(a)); }
+    m->launches++;
+    launch_colsum(m, m->rowbuf, B, m->n_small, m->n_small, nullptr, part + pl.off_rows, pl.Cb, side);
+    if (m->cfg.inner_conv) {
+      InnerDenseGradArgs d;
+      d.ids = ids; d.B = B; d.F = F; d.P = P; d.K = m->Ki; d.lgK = ilog2(m->Ki);
+      d.tab = tv.inner; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
+      d.pair_i = m->pair_i; d.pair_j = m->pair_j; d.partial = part + pl.off_Wd; d.C = pl.Cb;
+      dim3 grid(ceil_div((int64_t)P * m->Ki / 2, 256), pl.Cb);
+      CFFM_PROF(m, "inner_dense_grad", side);
+      CFFM_DISPATCH_ACT(act, k_inner_dense_grad<ACT><<<grid, 256, 0, side>>>(d));
+      m->launches++;
+    }
+    if (m->cfg.linear_att) {
+      dim3 grid(ceil_div(F * F, 256), pl.Cb);
+      CFFM_PROF(m, "att_outer", side);
+      k_att_outer<<<grid, 256, 0, side>>>(m->fb_buf, m->rowbuf, B, F, m->n_small, part + pl.off_attW, pl.Cb);
+      m->launches++;
+    }
+  }
+  // one GPU: the sort of the step's ids needs nothing but the ids
+  const bool sort_on_side = m->world == 1 && !sharded(m);
+  if (sort_on_side) {
+    int r;
+    { CFFM_PROF(m, "sort_segments", side); r = sparse_sort_segments(&m->sw, ids, (int64_t)B * F, m->M, side, &m->launches); }
+    if (r != CFFM_OK) { m->err = "sparse_sort_segments failed"; return r; }
+  }
   // ---- head ----
   launch_colsum(m, m->gout, B, 1, 1, nullptr, part + pl.off_G, pl.Cb, s);
   if (m->cfg.outer_conv) {
@@ -634,39 +674,8 @@ int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, in
       }
     }
   }
-  // ---- inner path + linear term ----
-  {
-    InnerLinBwdArgs a;
-    a.ids = ids; a.B = B; a.F = F; a.P = P; a.K = m->cfg.inner_conv ? m->Ki : 4; a.lgK = ilog2(a.K);
-    a.n_small = m->n_small; a.inner_conv = m->cfg.inner_conv; a.linear_att = m->cfg.linear_att;
-    a.tab = tv.inner; a.fbias = tv.fbias; a.cw = w + L.iconv_w; a.cb = w + L.iconv_b; a.Wd = w + L.din_k;
-    a.attW = w + L.att_W; a.attb = w + L.att_b; a.w3 = w + L.d3_k;
-    a.pair_i = m->pair_i; a.pair_j = m->pair_j; a.tau = m->cfg.lamda_att; a.gout = m->gout;
-    a.g_inner_rows = m->g_inner_rows; a.g_bias_rows = m->g_bias_rows; a.rowbuf = m->rowbuf;
-    int wpb = 8;
-    while (wpb > 1 && inner_bwd_smem(F, P, a.K, wpb) > 96 * 1024) wpb >>= 1;
-    { CFFM_PROF(m, "inner_linear_bwd", s);
-    CFFM_DISPATCH_ACT(act, k_inner_linear_bwd<ACT><<<ceil_div(B, wpb), wpb * 32, inner_bwd_smem(F, P, a.K, wpb), s>>>(a)); }
-    m->launches++;
-    launch_colsum(m, m->rowbuf, B, m->n_small, m->n_small, nullptr, part + pl.off_rows, pl.Cb, s);
-    if (m->cfg.inner_conv) {
-      InnerDenseGradArgs d;
-      d.ids = ids; d.B = B; d.F = F; d.P = P; d.K = m->Ki; d.lgK = ilog2(m->Ki);
-      d.tab = tv.inner; d.cw = w + L.iconv_w; d.cb = w + L.iconv_b; d.gout = m->gout;
-      d.pair_i = m->pair_i; d.pair_j = m->pair_j; d.partial = part + pl.off_Wd; d.C = pl.Cb;
-      dim3 grid(ceil_div((int64_t)P * m->Ki / 2, 256), pl.Cb);
-      CFFM_PROF(m, "inner_dense_grad", s);
-      CFFM_DISPATCH_ACT(act, k_inner_dense_grad<ACT><<<grid, 256, 0, s>>>(d));
-      m->launches++;
-    }
-    if (m->cfg.linear_att) {
-      dim3 grid(ceil_div(F * F, 256), pl.Cb);
-      CFFM_PROF(m, "att_outer", s);
-      k_att_outer<<<grid, 256, 0, s>>>(m->fb_buf, m->rowbuf, B, F, m->n_small, part + pl.off_attW, pl.Cb);
-      m->launches++;
-    }
-  }
   // ---- fold the partial sums into the dense gradient block, then the derived head gradients ----
+  { int r = side_join(m, side, s); if (r != CFFM_OK) return r; }
   {
     dim3 grid(2 * 148, m->n_reduce_descs);
     { CFFM_PROF(m, "reduce_partials", s);
@@ -720,8 +729,8 @@ int run_backward_update(Model* m, const int32_t* ids_in, const float* labels, in
   }
   // ---- sparse update of the three tables (one sort shared by all of them) ----
   {
-    int r;
-    { CFFM_PROF(m, "sort_segments", s); r = sparse_sort_segments(&m->sw, upd_ids, n_upd, m->M, s, &m->launches); }
+    int r = CFFM_OK;
+    if (!sort_on_side) { CFFM_PROF(m, "sort_segments", s); r = sparse_sort_segments(&m->sw, upd_ids, n_upd, m->M, s, &m->launches); }
     if (r != CFFM_OK) { m->err = "sparse_sort_segments failed"; return r; }
     const int opt = m->cfg.optimizer;
     const bool adam = opt == CFFM_OPT_ADAM;

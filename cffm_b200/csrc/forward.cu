@@ -308,6 +308,7 @@ int run_forward(Model* m, const int32_t* ids_in, const float* labels, int64_t B6
   m->view = tv;
   const int32_t* ids = tv.ids;
   // ---- inner path + linear term ----
+  cudaStream_t side = s;
   {
     InnerLinArgs a;
     a.ids = ids; a.B = B; a.F = F; a.P = P; a.K = m->cfg.inner_conv ? m->Ki : 4; a.lgK = ilog2(a.K);
@@ -320,9 +321,10 @@ int run_forward(Model* m, const int32_t* ids_in, const float* labels, int64_t B6
     int wpb = 8;
     while (wpb > 1 && inner_smem(F, P, a.K, wpb) > 96 * 1024) wpb >>= 1;
     const size_t smem = inner_smem(F, P, a.K, wpb);
-    CFFM_PROF(m, "inner_linear_fwd", s);
+    side = side_fork(m, s);   // joined before the head
+    CFFM_PROF(m, "inner_linear_fwd", side);
     CFFM_DISPATCH_ACT(m->cfg.activation,
-      k_inner_linear_fwd<ACT><<<ceil_div(B, wpb), wpb * 32, smem, s>>>(a));
+      k_inner_linear_fwd<ACT><<<ceil_div(B, wpb), wpb * 32, smem, side>>>(a));
     m->launches++;
   }
   // ---- outer path ----
@@ -368,6 +370,7 @@ int run_forward(Model* m, const int32_t* ids_in, const float* labels, int64_t B6
     }
   }
   // ---- head + loss terms ----
+  { int r = side_join(m, side, s); if (r != CFFM_OK) return r; }
   {
     HeadArgs a;
     a.B = B; a.t1_dim = m->t1_dim; a.inner_conv = m->cfg.inner_conv; a.outer_conv = m->cfg.outer_conv;

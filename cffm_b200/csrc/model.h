@@ -60,6 +60,12 @@ struct Model {
   int max_batch;
   int device;
   cudaStream_t stream = nullptr;
+  // The inner path + linear term (and, on one GPU, the sort of the step's ids) do not depend on the outer path until
+  // the head / the update: they run on a side stream forked from and joined to the step's stream -- inside a stream
+  // capture a parallel branch of the step graph.  At the reference's dataset shapes (a few dozen CTAs per kernel) the
+  // branches really overlap.  CFFM_SIDE_STREAM=0 keeps everything on one stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int64_t launches = 0;
 
@@ -189,6 +195,11 @@ int comm_allgather(Model* m, const void* send, void* recv, int64_t bytes_per_ran
 int comm_group_begin(Model* m);
 int comm_group_end(Model* m);
 void comm_destroy(Model* m);
+
+// side_fork: the side stream, ordered after everything enqueued on `s` so far (or `s` itself when there is none);
+// side_join: `s` continues after everything enqueued on the side stream
+cudaStream_t side_fork(Model* m, cudaStream_t s);
+int side_join(Model* m, cudaStream_t side, cudaStream_t s);
 
 // Brackets one launch with CUDA events on its stream when profiling is enabled.
 struct ProfScope {

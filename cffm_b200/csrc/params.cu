@@ -333,6 +333,14 @@ int model_alloc(Model* m) {
   const int64_t B = m->max_batch, F = m->F, P = m->P, M = m->Mloc;
   CFFM_CUDA_OK(m, cudaSetDevice(m->device));
   CFFM_CUDA_OK(m, cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("CFFM_SIDE_STREAM");
+    if (!(e && !strcmp(e, "0"))) {
+      CFFM_CUDA_OK(m, cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+      CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    }
+  }
   if (m->cfg.inner_conv) { TRY(dmalloc(m, &m->inner_tab, M * m->Ki)); TRY(dmalloc(m, &m->inner_acc, M * m->Ki)); }
   if (m->cfg.outer_conv) { TRY(dmalloc(m, &m->outer_tab, M * m->Ko)); TRY(dmalloc(m, &m->outer_acc, M * m->Ko)); }
   TRY(dmalloc(m, &m->fbias_tab, M)); TRY(dmalloc(m, &m->fbias_acc, M));
@@ -395,6 +403,7 @@ int model_alloc(Model* m) {
 void model_free(Model* m) {
   if (m->device >= 0) cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->side) cudaStreamSynchronize(m->side);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   void* dev[] = {m->inner_tab, m->outer_tab, m->fbias_tab, m->inner_acc, m->outer_acc, m->fbias_acc, m->dense_w,
                  m->dense_acc, m->dense_g, m->pair_i, m->pair_j, m->ids_buf, m->labels_buf, m->outer_rows, m->t1,
@@ -416,7 +425,26 @@ void model_free(Model* m) {
     if (m->slot_done[s]) cudaEventDestroy(m->slot_done[s]);
   }
   if (m->h_out) cudaFreeHost(m->h_out);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->side) cudaStreamDestroy(m->side);
   if (m->stream) cudaStreamDestroy(m->stream);
+}
+
+cudaStream_t side_fork(Model* m, cudaStream_t s) {
+  if (!m->side) return s;
+  if (cudaEventRecord(m->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(m->side, m->ev_fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return s;   // nothing has been enqueued on the side stream: the step stays on one stream
+  }
+  return m->side;
+}
+
+int side_join(Model* m, cudaStream_t side, cudaStream_t s) {
+  if (side == s) return CFFM_OK;
+  CFFM_CUDA_OK(m, cudaEventRecord(m->ev_join, side));
+  CFFM_CUDA_OK(m, cudaStreamWaitEvent(s, m->ev_join, 0));
+  return CFFM_OK;
 }
 
 }  // namespace cffm
