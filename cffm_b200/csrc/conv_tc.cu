@@ -1295,6 +1295,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
   TCState* st = reinterpret_cast<TCState*>(m->tcs);
   const int K = m->Ko, Pp = st->Pp, P = m->P;
   float* g = m->dense_g;
+  cudaStream_t wside = s;   // the side stream the weight gradients were put on, if any
   int lvl_off[kMaxConv + 1]; lvl_off[0] = 0;
   for (int l = 0; l < m->conv_depth; ++l) lvl_off[l + 1] = lvl_off[l] + (K >> l);
   {  // top of the stack
@@ -1309,7 +1310,32 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
   // Bias gradients d b_l = column sums of dY_l.  Big batches: per layer, right when dY_l has been written (it is still in
   // L2).  Small batches (the reference's datasets): all layers in one launch pair after the loop -- at those sizes the
   // eight launches cost more than the sums.
-  const bool colsum_late = (int64_t)B * (K / 2) * (K / 2) * Pp * 2 <= (int64_t)48 << 20;
+  const bool colsum_late = small_step(m, B);
+  // small batches: the column sums of all layers in one launch pair, once every dY_l is complete
+  auto colsum_all_layers = [&](cudaStream_t cs) {
+    CFFM_PROF(m, "colsum", cs);
+    ColsumLayers a;
+    memset(&a, 0, sizeof(a));
+    a.Pp = Pp; a.n = P; a.partial = st->bg_partial; a.partial_stride = (int64_t)2 * 148 * P;
+    int maxC = 1, nl = 0;
+    for (int l = 0; l < m->n_live; ++l) {
+      if (l == 0 && st->df_bpart && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
+      const int64_t rows = (int64_t)B * (K >> (l + 1)) * (K >> (l + 1));
+      a.X[nl] = st->dY[l]; a.Xlo[nl] = st->dYlo[l]; a.rows[nl] = rows;
+      a.C[nl] = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));   // few chunks: the second stage walks them one by one
+      a.out_off[nl] = m->lay.conv_b[l];
+      maxC = std::max(maxC, a.C[nl]);
+      ++nl;
+    }
+    a.n_layers = nl;
+    if (nl > 0) {
+      const int CG = Pp / 8;
+      int R = 512 / CG; if (R < 1) R = 1; if (R > 32) R = 32;
+      k_colsum_bf16_layers<<<dim3(maxC, nl), CG * R, sizeof(float) * R * Pp, cs>>>(a);
+      k_sum_chunks_layers<<<dim3(ceil_div(P, 128), nl), 128, 0, cs>>>(a, g);
+      m->launches += 2;
+    }
+  };
   for (int l = m->n_live - 1; l >= 0; --l) {
     const Geom gm = make_geom(m, st, B, l);
     const int64_t rows = gm.M;
@@ -1322,9 +1348,12 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       k_sum_chunks<<<ceil_div(P, 128), 128, 0, s>>>(st->bg_partial, P, C, g + m->lay.conv_b[l]);
       m->launches += 2;
     }
-    {  // weight gradient
+    {  // weight gradient: beside the data-gradient chain (side stream 1: dY_l is complete on `s` at this point; the
+       // weight gradients of the layers follow one another there, so they can share their split-reduction scratch)
       const std::string tag = "conv_wgrad_l" + std::to_string(l);
-      CFFM_PROF(m, tag.c_str(), s);
+      const cudaStream_t ws = colsum_late ? side_fork(m, s, 1) : s;   // (colsum_late = small_step: see model.h)
+      if (ws != s) wside = ws;
+      CFFM_PROF(m, tag.c_str(), ws);
       const int rows_per_unit = l == 0 ? 2 * BM : BM;
       const int tiles = (4 * Pp / rows_per_unit) * gm.tiles_n;
       const int chunks_total = (int)((rows + BK - 1) / BK);
@@ -1344,7 +1373,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       if (l == 0 && st->wf_part && B >= st->fact_min_batch) {
         Wgrad0FactParams p;
         const int B8 = (B + 7) / 8 * 8, KP = st->nblk * 64;
-        k_build_a8<<<148 * 4, 256, 0, s>>>(m->outer_rows, B, B8, m->F, KP, st->A8, st->A8lo);
+        k_build_a8<<<148 * 4, 256, 0, ws>>>(m->outer_rows, B, B8, m->F, KP, st->A8, st->A8lo);
         memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2));
         TC_MAP_OK(m, mat_map(st, &p.mapA, st->A8, (int64_t)B8 * 16, KP, BM, 64));
         if (SPLIT) TC_MAP_OK(m, mat_map(st, &p.mapA2, st->A8lo, (int64_t)B8 * 16, KP, BM, 64));
@@ -1358,10 +1387,10 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
           attr_done = true;
         }
         const int units = (st->Q16 / W0_QS) * p.nsplit;
-        k_wgrad0_fact<SPLIT><<<units < 148 ? units : 148, W0_THREADS, w0_smem(SPLIT), s>>>(p);
+        k_wgrad0_fact<SPLIT><<<units < 148 ? units : 148, W0_THREADS, w0_smem(SPLIT), ws>>>(p);
         const int64_t tot = 4ll * P * P;
         int rb = (int)((tot + 255) / 256); if (rb > 148 * 8) rb = 148 * 8;
-        k_wfact_reduce<<<rb, 256, 0, s>>>(st->wf_part, m->pair_i, m->pair_j, P, st->KA, st->Q16, p.nsplit, g + m->lay.conv_w[0]);
+        k_wfact_reduce<<<rb, 256, 0, ws>>>(st->wf_part, m->pair_i, m->pair_j, P, st->KA, st->Q16, p.nsplit, g + m->lay.conv_w[0]);
         m->launches += 3;
         CFFM_CUDA_OK(m, cudaGetLastError());
       } else if (l == 0) {
@@ -1372,7 +1401,7 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
         memset(&p.mapA, 0, sizeof(p.mapA)); memset(&p.mapA2, 0, sizeof(p.mapA2)); memset(&p.mapB2, 0, sizeof(p.mapB2));
         TC_MAP_OK(m, mat_map(st, &p.mapB, st->dY[0], rows, Pp, 64, 64));
         if (st->split) TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[0], rows, Pp, 64, 64));
-        TCTRY(launch_tc(m, p, tiles * n_split, s));
+        TCTRY(launch_tc(m, p, tiles * n_split, ws));
       } else {
         ConvWgradTC<ACT, false, SPLIT> p;
         p.g = gm; p.chunks_total = chunks_total; p.chunks_per_split = cps; p.n_split = n_split; p.partial = st->wg_partial;
@@ -1385,12 +1414,12 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
           TC_MAP_OK(m, im2col_map(st, &p.mapA2, st->Xlo[l], B, gm.Hin, Pp, 64));
           TC_MAP_OK(m, mat_map(st, &p.mapB2, st->dYlo[l], rows, Pp, 64, 64));
         }
-        TCTRY(launch_tc(m, p, tiles * n_split, s));
+        TCTRY(launch_tc(m, p, tiles * n_split, ws));
       }
       if (!(l == 0 && st->wf_part && B >= st->fact_min_batch)) {
         const int64_t total = 4ll * P * P;
         int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-        k_wgrad_reduce<<<blocks, 256, 0, s>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
+        k_wgrad_reduce<<<blocks, 256, 0, ws>>>(st->wg_partial, n_split, P, Pp, l == 0 ? 1 : 0, g + m->lay.conv_w[l]);
         m->launches++;
       }
     }
@@ -1428,31 +1457,10 @@ static int conv_backward_act(Model* m, int B, cudaStream_t s) {
       }
     }
   }
-  if (colsum_late) {
-    CFFM_PROF(m, "colsum", s);
-    ColsumLayers a;
-    memset(&a, 0, sizeof(a));
-    a.Pp = Pp; a.n = P; a.partial = st->bg_partial; a.partial_stride = (int64_t)2 * 148 * P;
-    int maxC = 1, nl = 0;
-    for (int l = 0; l < m->n_live; ++l) {
-      if (l == 0 && st->df_bpart && B >= st->fact_min_batch) continue;   // collected by k_dgrad0_fact
-      const int64_t rows = (int64_t)B * (K >> (l + 1)) * (K >> (l + 1));
-      a.X[nl] = st->dY[l]; a.Xlo[nl] = st->dYlo[l]; a.rows[nl] = rows;
-      a.C[nl] = (int)std::min<int64_t>(64, std::max<int64_t>(1, (rows + 63) / 64));   // few chunks: the second stage walks them one by one
-      a.out_off[nl] = m->lay.conv_b[l];
-      maxC = std::max(maxC, a.C[nl]);
-      ++nl;
-    }
-    a.n_layers = nl;
-    if (nl > 0) {
-      const int CG = Pp / 8;
-      int R = 512 / CG; if (R < 1) R = 1; if (R > 32) R = 32;
-      k_colsum_bf16_layers<<<dim3(maxC, nl), CG * R, sizeof(float) * R * Pp, s>>>(a);
-      k_sum_chunks_layers<<<dim3(ceil_div(P, 128), nl), 128, 0, s>>>(a, g);
-      m->launches += 2;
-    }
-  }
-  return CFFM_OK;
+  // (on the side stream after layer 0's weight gradient they cost 14 us of a 190 us Frappe step; so did the filters'
+  // operand copies beside the gather: a branch is worth it from a few tens of microseconds of work)
+  if (colsum_late) colsum_all_layers(s);
+  return side_join(m, wside, s, 1);
 }
 
 int tc_conv_backward(Model* m, int B, cudaStream_t s) {

@@ -60,12 +60,13 @@ struct Model {
   int max_batch;
   int device;
   cudaStream_t stream = nullptr;
-  // The inner path + linear term (and, on one GPU, the sort of the step's ids) do not depend on the outer path until
-  // the head / the update: they run on a side stream forked from and joined to the step's stream -- inside a stream
-  // capture a parallel branch of the step graph.  At the reference's dataset shapes (a few dozen CTAs per kernel) the
-  // branches really overlap.  CFFM_SIDE_STREAM=0 keeps everything on one stream.
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Side streams, forked from and joined to the step's stream -- inside a stream capture parallel branches of the step
+  // graph.  [0]: the inner path + linear term (and, on one GPU, the sort of the step's ids), which do not depend on the
+  // outer path until the head / the update; [1]: on small steps the weight gradients of the conv stack, which nothing
+  // waits for until the dense update, beside the chain of data gradients.  At the reference's dataset shapes (a few dozen CTAs per
+  // kernel) the branches really overlap.  CFFM_SIDE_STREAM=0 keeps everything on one stream.
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   std::string err;
   int64_t launches = 0;
 
@@ -198,8 +199,16 @@ void comm_destroy(Model* m);
 
 // side_fork: the side stream, ordered after everything enqueued on `s` so far (or `s` itself when there is none);
 // side_join: `s` continues after everything enqueued on the side stream
-cudaStream_t side_fork(Model* m, cudaStream_t s);
-int side_join(Model* m, cudaStream_t side, cudaStream_t s);
+// Small steps (layer 0's gradient tensor within 48 MB: the reference's dataset shapes) are a chain of kernels of a few
+// dozen CTAs: there the tensor-core kernels of one step are put on parallel branches too.  Big steps keep them on one
+// stream: the persistent kernels count on all their CTAs running together (L2 sharing between neighbouring CTAs), and two
+// of them competing for the SMs measured 59.8 -> 70.7 ms at the Criteo shape.
+inline bool small_step(const Model* m, int64_t B) {
+  const int64_t H = m->Ko / 2, Pp = (m->P + 63) & ~63;
+  return B * H * H * Pp * 2 <= ((int64_t)48 << 20);
+}
+cudaStream_t side_fork(Model* m, cudaStream_t s, int which = 0);
+int side_join(Model* m, cudaStream_t side, cudaStream_t s, int which = 0);
 
 // Brackets one launch with CUDA events on its stream when profiling is enabled.
 struct ProfScope {

@@ -336,9 +336,11 @@ int model_alloc(Model* m) {
   {
     const char* e = getenv("CFFM_SIDE_STREAM");
     if (!(e && !strcmp(e, "0"))) {
-      CFFM_CUDA_OK(m, cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
-      CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-      CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+      for (int i = 0; i < 2; ++i) {
+        CFFM_CUDA_OK(m, cudaStreamCreateWithFlags(&m->side[i], cudaStreamNonBlocking));
+        CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_fork[i], cudaEventDisableTiming));
+        CFFM_CUDA_OK(m, cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+      }
     }
   }
   if (m->cfg.inner_conv) { TRY(dmalloc(m, &m->inner_tab, M * m->Ki)); TRY(dmalloc(m, &m->inner_acc, M * m->Ki)); }
@@ -403,7 +405,7 @@ int model_alloc(Model* m) {
 void model_free(Model* m) {
   if (m->device >= 0) cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
-  if (m->side) cudaStreamSynchronize(m->side);
+  for (int i = 0; i < 2; ++i) if (m->side[i]) cudaStreamSynchronize(m->side[i]);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   void* dev[] = {m->inner_tab, m->outer_tab, m->fbias_tab, m->inner_acc, m->outer_acc, m->fbias_acc, m->dense_w,
                  m->dense_acc, m->dense_g, m->pair_i, m->pair_j, m->ids_buf, m->labels_buf, m->outer_rows, m->t1,
@@ -425,25 +427,27 @@ void model_free(Model* m) {
     if (m->slot_done[s]) cudaEventDestroy(m->slot_done[s]);
   }
   if (m->h_out) cudaFreeHost(m->h_out);
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-  if (m->ev_join) cudaEventDestroy(m->ev_join);
-  if (m->side) cudaStreamDestroy(m->side);
+  for (int i = 0; i < 2; ++i) {
+    if (m->ev_fork[i]) cudaEventDestroy(m->ev_fork[i]);
+    if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+    if (m->side[i]) cudaStreamDestroy(m->side[i]);
+  }
   if (m->stream) cudaStreamDestroy(m->stream);
 }
 
-cudaStream_t side_fork(Model* m, cudaStream_t s) {
-  if (!m->side) return s;
-  if (cudaEventRecord(m->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(m->side, m->ev_fork, 0) != cudaSuccess) {
+cudaStream_t side_fork(Model* m, cudaStream_t s, int which) {
+  if (!m->side[which]) return s;
+  if (cudaEventRecord(m->ev_fork[which], s) != cudaSuccess || cudaStreamWaitEvent(m->side[which], m->ev_fork[which], 0) != cudaSuccess) {
     cudaGetLastError();
-    return s;   // nothing has been enqueued on the side stream: the step stays on one stream
+    return s;   // nothing has been enqueued on the side stream: the work stays on the step's stream
   }
-  return m->side;
+  return m->side[which];
 }
 
-int side_join(Model* m, cudaStream_t side, cudaStream_t s) {
+int side_join(Model* m, cudaStream_t side, cudaStream_t s, int which) {
   if (side == s) return CFFM_OK;
-  CFFM_CUDA_OK(m, cudaEventRecord(m->ev_join, side));
-  CFFM_CUDA_OK(m, cudaStreamWaitEvent(s, m->ev_join, 0));
+  CFFM_CUDA_OK(m, cudaEventRecord(m->ev_join[which], side));
+  CFFM_CUDA_OK(m, cudaStreamWaitEvent(s, m->ev_join[which], 0));
   return CFFM_OK;
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-for ss in 1 0; do
+for ss in 1; do
   echo "== CFFM_SIDE_STREAM=$ss"
   CFFM_SIDE_STREAM=$ss timeout 300 python bench.py --steps 10 --warmup 3 --modes bf16 --no-cpu-baseline > gpurun_out/zz_bench_$ss.json 2> gpurun_out/zz_bench_$ss.err
   python - <<PY
