@@ -1,3 +1,6 @@
 #!/bin/bash
 cd /root/repo
-for rep in 1 2; do for mk in 0 1 3 7 11 15; do CFFM_SIDE_MASK=$mk timeout 120 python scratch/small_bench.py bf16 2>&1 | tail -n 1; done; done
+mkdir -p gpurun_out
+timeout 120 python scratch/small_bench.py bf16 2>&1 | tail -n 1
+timeout 120 python scratch/small_bench.py bf16x3 2>&1 | tail -n 1
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/z_pytest_gpu.log 2>&1; echo "gpu suite rc=$?"; tail -n 3 gpurun_out/z_pytest_gpu.log
