@@ -1,5 +1,6 @@
 #!/bin/bash
 cd /root/repo
-timeout 120 python scratch/small_bench.py bf16 2>&1 | tail -n 1
-timeout 120 python scratch/small_time.py frappe bf16 2>&1 | grep -i "colsum\|total"
-timeout 300 python -m pytest tests/test_gpu_branches.py tests/test_gpu_parity.py tests/test_gpu_bf16.py tests/test_gpu_bf16x3.py -q -x 2>&1 | tail -n 2
+for p in bf16 bf16x3; do
+echo -n "default     "; timeout 120 python scratch/small_bench.py $p 2>&1 | tail -n 1
+echo -n "factorised  "; CFFM_FACT_MIN_FIELDS=1 CFFM_FACT_MIN_BATCH=1 timeout 120 python scratch/small_bench.py $p 2>&1 | tail -n 1
+done
